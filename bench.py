@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""Benchmark of the DAGTracer hot path (BASELINE.json metric: Mrays/s primary+shadow on a depth-17
+HashDAG at 1080p / 4K, with the achieved fraction of the HBM gather roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference ...                            # the algorithm on the host cores (CPU arm)
+    python bench.py --impl reference-cuda ...                       # the reference's own CUDA kernels, same frames (1 GPU)
+
+A step is one frame of the seeded fly-through: resolve_paths + resolve_colors + resolve_shadows.
+rays per step = W*H primary + one shadow ray per hit pixel.  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/s primary+shadow (depth-17 HashDAG)"
+UNIT = "Mrays/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
+    ap.add_argument("--levels", type=int, default=17)
+    ap.add_argument("--footprint-log2", type=int, default=int(os.environ.get("HDT_BENCH_FOOTPRINT", "14")))
+    ap.add_argument("--poses", type=int, default=64)
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--cpu-sample-poses", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dag", default="hash", choices=["hash", "basic"])
+    return ap.parse_args()
+
+
+def resolution(args, world):
+    if args.width and args.height:
+        return args.width, args.height
+    return (1920, 1080) if world == 1 else (3840, 2160)   # configs[1] / configs[2]
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+        out["reasons"], out["samples"] = sorted(reasons), len(sm)
+        return out
+
+
+def algorithmic_bytes(stats_paths, stats_colors, stats_shadows, hash_dag, w, h):
+    """bytes the reference algorithm touches per frame, per pass."""
+    def walk(st):
+        return 4 * st["n_word"] + 8 * st["n_leaf"] + (4 * st["n_page"] if hash_dag else 0)
+    px = w * h
+    return {
+        "paths": walk(stats_paths) + 16 * px,
+        "colors": walk(stats_colors) + 8 * stats_colors["n_color_probe"] + 16 * px + 4 * px,
+        "shadows": walk(stats_shadows) + (16 + 4 + 4) * px,
+    }
+
+
+def oracle_frame(hdo, odag, ocol, params, w, h, threads=0):
+    t0 = time.perf_counter()
+    p, sp = hdo.trace_paths(odag, w, h, params, threads)
+    c, sc = hdo.trace_colors(odag, ocol, p, n_threads=threads)
+    s, ss = hdo.trace_shadows(odag, params, p, c, 1.0, 0.0, threads)
+    dt = time.perf_counter() - t0
+    return dt, w * h + sp["n_hit"], (sp, sc, ss), s
+
+
+def run_reference_cpu(args):
+    """--impl reference: the algorithm restated for the host (oracle/, kind "port"; the reference has no
+    host implementation of its __device__ traversal) on every host thread.  Each step is a
+    quarter-resolution frame of the same fly-through so the run stays within minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hashdag_b200 import camera, workloads
+    from oracle import hdo
+    W, H = resolution(args, args.gpus)
+    w, h = W // 4, H // 4
+    scene, poses = workloads.build_workload(args.levels, args.footprint_log2, args.poses)
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    hashed = args.dag == "hash"
+    odag = hdo.make_dag(scene, hdo.DAG_HASH if hashed else hdo.DAG_BASIC)
+    ocol = hdo.make_colors(scene, hdo.COLORS_HASH if hashed else hdo.COLORS_COMPRESSED)
+    cores = os.cpu_count() or 1
+    rays, secs = 0, 0.0
+    for i in range(args.warmup + args.steps):
+        prm = camera.trace_params(poses[i % len(poses)], info, scene.levels, w, h)
+        dt, n, _, _ = oracle_frame(hdo, odag, ocol, prm, w, h)
+        if i >= args.warmup:
+            rays += n
+            secs += dt
+    value = rays / secs / 1e6
+    sample = f"{args.steps} frames at {w}x{h} (1/16 of the {W}x{H} rays per frame), same DAG and camera path, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32+f64+u32", "data": "synthetic",
+        "config": workload_config(args, scene, W, H, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, scene, W, H, world):
+    return {
+        "workload": f"synthetic depth-{args.levels} {'HashDAG' if args.dag == 'hash' else 'BasicDAG'} terrain (footprint 2^{args.footprint_log2}, seed 1337), "
+                    f"{W}x{H} primary+shadow+colour, {args.poses}-pose fly-through",
+        "levels": args.levels, "resolution": [W, H], "voxels": int(scene.n_voxels), "dag_words": int(scene.basic.size),
+        "hash_pool_mib": round(scene.hash_pool.nbytes / 2**20, 1) if scene.has_hash else 0,
+        "color_mib": round((scene.weights.nbytes + scene.blocks.nbytes + scene.macro_blocks.nbytes) / 2**20, 1),
+        "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, NCCL gather to rank 0",
+        "l2_policy": "inputs larger than L2: each step is a different camera pose over a DAG pool >> 126 MB",
+        "shadow_bias": 1.0, "fog_density": 0.0,
+    }
+
+
+def run_reference_cuda(args):
+    """Extra arm (not part of the driver contract): the UNMODIFIED reference kernels from oracle/_ref
+    on the same GPU, DAG and camera path -- the number the north star's '>= 5x' refers to."""
+    from hashdag_b200 import camera, workloads
+    from oracle import ref
+    W, H = resolution(args, 1)
+    scene, poses = workloads.build_workload(args.levels, args.footprint_log2, args.poses)
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    rt = ref.RefTracer(args.levels, W, H)
+    rt.load_scene(scene)
+    hashed = args.dag == "hash"
+    dk, ck = (1, 3) if hashed else (0, 1)
+    hits = []
+    for pose in poses:   # untimed: shadow rays per pose
+        rt.resolve_paths(dk, pose, info)
+        hits.append(int(rt.read_paths()[..., :3].any(-1).sum()))
+    tp = tc = ts = 0.0
+    rays = 0
+    for i in range(args.warmup + args.steps):
+        pose = poses[i % len(poses)]
+        a = rt.resolve_paths(dk, pose, info)
+        b = rt.resolve_colors(dk, ck)
+        c = rt.resolve_shadows(dk, pose, info, 1.0, 0.0)
+        if i >= args.warmup:
+            tp, tc, ts = tp + a, tc + b, ts + c
+            rays += W * H + hits[i % len(poses)]
+    total_ms = tp + tc + ts
+    print(json.dumps({
+        "impl": "reference-cuda", "metric": METRIC, "value": rays / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "dtype": "f32+f64+u32", "data": "synthetic",
+        "config": workload_config(args, scene, W, H, 1),
+        "passes_ms": {"paths": tp / args.steps, "colors": tc / args.steps, "shadows": ts / args.steps},
+        "mrays_s_paths_shadows_only": rays / ((tp + ts) * 1e-3) / 1e6,
+        "note": "kernel times from the reference's own cudaEvents (dag_tracer.cu:130-138), summed; each call is synchronous",
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hashdag_b200 import camera, tracer, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the tracer has no CPU path (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    W, H = resolution(args, world)
+    hashed = args.dag == "hash"
+
+    # ---- scene: rank 0 builds, the replicas get it over NCCL -------------------------------
+    t_build = time.perf_counter()
+    scene = poses = None
+    if rank == 0:
+        scene, poses = workloads.build_workload(args.levels, args.footprint_log2, args.poses)
+    if world > 1:
+        box = [scene_meta(scene, poses) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        meta = box[0]
+        tensors = {}
+        for name, (n, itemsize) in meta["arrays"].items():
+            dt = torch.int32 if itemsize == 4 else torch.int64
+            if rank == 0:
+                arr = getattr(scene, name)
+                t = torch.from_numpy(arr.view(np.int32 if itemsize == 4 else np.int64)).to(dev)
+            else:
+                t = torch.empty(n, dtype=dt, device=dev)
+            dist.broadcast(t, src=0)
+            tensors[name] = t
+        if rank != 0:
+            poses = [camera.CameraView(tuple(p[0]), tuple(tuple(r) for r in p[1])) for p in meta["poses"]]
+        dag, colors = replicas_from_tensors(tracer, tensors, meta, hashed)
+        bounds = (tuple(meta["bounds_min"]), tuple(meta["bounds_max"]))
+        replication_bytes = sum(n * isz for n, isz in meta["arrays"].values())
+    else:
+        if hashed:
+            dag, colors = tracer.HashDAG.from_scene(scene, dev), tracer.HashDAGColors.from_scene(scene, dev)
+        else:
+            dag, colors = tracer.BasicDAG.from_scene(scene, dev), tracer.BasicDAGCompressedColors.from_scene(scene, dev)
+        bounds = (scene.bounds_min, scene.bounds_max)
+        replication_bytes = 0
+    t_build = time.perf_counter() - t_build
+    info = camera.DAGInfo(*bounds)
+
+    tr = tracer.DAGTracer(True, W, H, args.levels, device=local_rank)
+    tile_log2 = 6
+    if world > 1:
+        tr.set_partition(rank, world, tile_log2)
+    params = [camera.trace_params(p, info, args.levels, W, H) for p in poses]
+    dag_pod, col_pod = dag.pod(), colors.pod()
+
+    # ---- multi-GPU gather plumbing ----------------------------------------------------------
+    gather = None
+    if world > 1:
+        _, cptr, n_owned, max_tiles = tr.partition_buffers()
+        n = max_tiles << (2 * tile_log2)
+
+        class _Mem:
+            def __init__(self, ptr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        mine = torch.as_tensor(_Mem(cptr, n), device=dev)
+        gathered = torch.empty(world * n, dtype=torch.int32, device=dev) if rank == 0 else None
+        frame = torch.empty(W * H, dtype=torch.int32, device=dev) if rank == 0 else None
+
+        def gather():
+            dist.gather(mine, list(gathered.chunk(world)) if rank == 0 else None, dst=0)
+            if rank == 0:
+                torch.cuda.current_stream().synchronize()
+                tr.assemble_colors(gathered, frame)
+    host_frame = torch.empty(W * H, dtype=torch.int32).pin_memory() if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        tr.enqueue_frame(params[i % len(params)], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+        if gather:
+            tr.sync()
+            gather()
+
+    # ---- hits per pose (untimed) -------------------------------------------------------------
+    hits = []
+    for i in range(len(params)):
+        tr.enqueue_frame(params[i], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, False, None)
+        tr.sync()
+        hits.append(tr.count_hits())
+    if world > 1:
+        ht = torch.tensor(hits, dtype=torch.int64, device=dev)
+        dist.all_reduce(ht)
+        hits = ht.tolist()
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    tr.sync()
+
+    # ---- timed: K steps, inputs resident, device time, max over ranks ----------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = tr.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    tr.timer_begin()
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    dev_ms = tr.timer_end()
+    if gather:
+        torch.cuda.synchronize()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    # with a gather in the loop part of the step runs on torch's stream: the barrier-to-barrier wall
+    # clock is then the honest number; single GPU uses the device events on the tracer's stream
+    elapsed_ms = dev_ms if not gather else wall_ms
+    launches = tr.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    rays = sum(W * H + hits[(args.warmup + i) % len(hits)] for i in range(args.steps))
+    value = rays / (elapsed_ms * 1e-3) / 1e6
+
+    # ---- e2e: public API, host camera in, colour frame out to pinned host memory, every step --
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        p = poses[(args.warmup + i) % len(poses)]
+        if world == 1:
+            tr.resolve_frame(p, info, dag, colors, 1.0, 0.0, True, host_frame)
+        else:
+            tr.resolve_frame(p, info, dag, colors, 1.0, 0.0, True, None)
+            gather()
+            if rank == 0:
+                host_frame.copy_(frame, non_blocking=False)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = rays / (e2e_ms * 1e-3) / 1e6
+
+    # ---- per-pass kernel times on the sample poses (for the roofline) ------------------------
+    sample_ids = [int(k * len(poses) / max(1, args.cpu_sample_poses)) for k in range(args.cpu_sample_poses)]
+    pass_ms = {i: [0.0, 0.0, 0.0] for i in sample_ids}
+    reps = 5
+    if world == 1:
+        for _ in range(reps):
+            for i in sample_ids:
+                ms = tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
+                for k in range(3):
+                    pass_ms[i][k] += ms[k] / reps
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32+f64+u32", "data": "synthetic",
+        "config": workload_config(args, scene, W, H, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 96, "d2h_bytes_per_step": W * H * 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "setup_s": round(t_build, 1), "scene_build_s": round(scene.build_seconds, 1), "replication_bytes": int(replication_bytes),
+        "timing": "cudaEvents on the tracer stream around K enqueued frames" if not gather else "barrier-to-barrier wall clock incl. NCCL gather + assembly, max over ranks",
+    }
+
+    # ---- CPU baseline + algorithmic bytes (bounded sample), roofline -------------------------
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import hdo
+        odag = hdo.make_dag(scene, hdo.DAG_HASH if hashed else hdo.DAG_BASIC)
+        ocol = hdo.make_colors(scene, hdo.COLORS_HASH if hashed else hdo.COLORS_COMPRESSED)
+        cores = os.cpu_count() or 1
+        cpu_rays, cpu_s = 0, 0.0
+        bytes_pass = {"paths": 0, "colors": 0, "shadows": 0}
+        gpu_ms_pass = {"paths": 0.0, "colors": 0.0, "shadows": 0.0}
+        mismatch = 0
+        for i in sample_ids:
+            dt, n, (sp, sc, ss), img = oracle_frame(hdo, odag, ocol, params[i], W, H)
+            cpu_rays += n
+            cpu_s += dt
+            b = algorithmic_bytes(sp, sc, ss, hashed, W, H)
+            for k, name in enumerate(("paths", "colors", "shadows")):
+                bytes_pass[name] += b[name]
+                gpu_ms_pass[name] += pass_ms[i][k]
+            tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, host_frame)
+            mismatch += int((host_frame.numpy().view(np.uint32).reshape(H, W) != img).sum())
+        out["cpu_baseline"] = {"value": cpu_rays / cpu_s / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{len(sample_ids)} full {W}x{H} frames (poses {sample_ids}) of the same fly-through, oracle/ on {cores} threads"}
+        out["parity_check_mismatched_pixels_vs_oracle"] = mismatch
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        dominant = max(gpu_ms_pass, key=lambda k: gpu_ms_pass[k])
+        ach = {k: (bytes_pass[k] / (gpu_ms_pass[k] * 1e-3) / 1e9 if gpu_ms_pass[k] > 0 else 0.0) for k in bytes_pass}
+        out["roofline"] = {"bound": "hbm", "kernel": f"trace_{dominant}_kernel", "achieved": ach[dominant], "peak": peak, "unit": "GB/s",
+                           "frac": ach[dominant] / peak, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": bytes_pass[dominant] / len(sample_ids),
+                           "avg_launch_ms": gpu_ms_pass[dominant] / len(sample_ids),
+                           "per_pass": {k: {"ms": gpu_ms_pass[k] / len(sample_ids), "algorithmic_GBps": ach[k],
+                                            "bytes_per_launch": bytes_pass[k] / len(sample_ids)} for k in bytes_pass}}
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def scene_meta(scene, poses):
+    names = ["hash_pool", "hash_page_table", "weights", "blocks", "macro_blocks", "color_nodes", "color_offsets", "basic", "enclosed_leaves"]
+    return {
+        "arrays": {n: (int(getattr(scene, n).size), int(getattr(scene, n).dtype.itemsize)) for n in names},
+        "levels": scene.levels, "top_levels": scene.top_levels, "pool_top": scene.hash_pool_top, "first": scene.hash_first_node_index,
+        "bounds_min": list(scene.bounds_min), "bounds_max": list(scene.bounds_max),
+        "poses": [[list(p.position), [list(r) for r in p.rotation]] for p in poses],
+    }
+
+
+def replicas_from_tensors(tracer, t, meta, hashed):
+    leaf = tracer.CompressedColorLeaf(t["weights"], t["blocks"], t["macro_blocks"], tracer.UNIQUE_OFFSET)
+    if hashed:
+        dag = tracer.HashDAG(t["hash_pool"], t["hash_page_table"], meta["pool_top"], meta["first"], meta["levels"])
+        return dag, tracer.HashDAGColors(t["color_nodes"], t["color_offsets"], leaf)
+    dag = tracer.BasicDAG(t["basic"], meta["levels"])
+    return dag, tracer.BasicDAGCompressedColors(meta["top_levels"], t["enclosed_leaves"], leaf)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_cpu(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

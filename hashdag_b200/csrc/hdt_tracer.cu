@@ -1,0 +1,670 @@
+// libhashdag_b200.so: kernels + C ABI of the B200-native DAG tracer (include/hashdag_b200.h).
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
+//        -Xcompiler -fPIC -shared   (see __graft_entry__.build()).
+#include "../../include/hashdag_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "hdt_colors.cuh"
+#include "hdt_device.cuh"
+
+using namespace hdt;
+
+static_assert(sizeof(hdt_basic_dag) == 16, "BasicDAG layout");
+static_assert(sizeof(hdt_hash_dag) == 32, "HashDAG layout");
+static_assert(sizeof(hdt_color_leaf) == 104, "CompressedColorLeaf layout");
+static_assert(sizeof(hdt_basic_compressed_colors) == 128, "BasicDAGCompressedColors layout");
+static_assert(sizeof(hdt_basic_uncompressed_colors) == 40, "BasicDAGUncompressedColors layout");
+static_assert(sizeof(hdt_basic_color_errors) == 288, "BasicDAGColorErrors layout");
+static_assert(sizeof(hdt_hash_colors) == 248, "HashDAGColors layout");
+static_assert(sizeof(hdt_tool_info) == 44, "ToolInfo layout");
+
+namespace {
+
+constexpr u32 kBlockThreads = 256;   // 8 warps, each an 8x4 pixel patch; CTA covers 32x8 pixels
+constexpr u32 kBlockW = 32, kBlockH = 8;
+
+// Which pixel does this thread own?  CTAs are numbered tile-major over the tiles this rank owns.
+__device__ __forceinline__ bool thread_pixel(const PixelMap& m, u32& x, u32& y)
+{
+    const u32 T = 1u << m.tileLog2, blocksX = T / kBlockW, blocksPerTile = blocksX * (T / kBlockH);
+    const u32 slot = blockIdx.x / blocksPerTile, b = blockIdx.x % blocksPerTile;
+    const u32 t = m.rank + slot * m.world;
+    const u32 tx = t % m.tilesX, ty = t / m.tilesX;
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    x = tx * T + (b % blocksX) * kBlockW + (warp & 3) * 8 + (lane & 7);
+    y = ty * T + (b / blocksX) * kBlockH + (warp >> 2) * 4 + (lane >> 3);
+    return x < m.width && y < m.height;
+}
+
+// ---------------------------------------------------------------------------------------------
+// trace_paths (tracer.cu:145-252).  Output pixel row r holds camera row height-1-r (:251).
+// ---------------------------------------------------------------------------------------------
+template <class DAG>
+__global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const CameraParams cam, const DAG dag, const u32 levels, const PixelMap map,
+                                                                    uint4* __restrict__ paths)
+{
+    __shared__ u8 lut[8 * 256];
+    fill_next_child_lut(lut);
+    __syncthreads();
+    u32 x, y;
+    if (!thread_pixel(map, x, y)) return;
+
+    double ddx, ddy, ddz;
+    primary_direction(cam, x, map.height - 1 - y, ddx, ddy, ddz);
+    Ray ray;
+    ray.ox = __double2float_rn(cam.cam[0]); ray.oy = __double2float_rn(cam.cam[1]); ray.oz = __double2float_rn(cam.cam[2]);
+    ray.dx = __double2float_rn(ddx); ray.dy = __double2float_rn(ddy); ray.dz = __double2float_rn(ddz);
+    ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
+    const u32 order = (ray.dx < 0.f ? 4u : 0u) + (ray.dy < 0.f ? 2u : 0u) + (ray.dz < 0.f ? 1u : 0u);
+
+    u32 px, py, pz;
+    traverse<DAG, true>(dag, levels, ray, lut, order, px, py, pz);
+    paths[map.index(x, y)] = make_uint4(px, py, pz, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// trace_colors (tracer.cu:254-451)
+// ---------------------------------------------------------------------------------------------
+template <class DAG>
+__global__ void __launch_bounds__(kBlockThreads) trace_colors_kernel(const DAG dag, const ColorsDev colors, const u32 levels, const ColorsParams prm,
+                                                                     const PixelMap map, const uint4* __restrict__ paths, u32* __restrict__ out)
+{
+    u32 x, y;
+    if (!thread_pixel(map, x, y)) return;
+    const u64 idx = map.index(x, y);
+    const uint4 p = paths[idx];
+    out[idx] = color_pixel(dag, colors, levels, prm, p.x, p.y, p.z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// trace_shadows (tracer.cu:589-697): exact hit point, any-hit ray towards the sun, shade, fog.
+// ---------------------------------------------------------------------------------------------
+struct ShadowParams { float shadowBias, fogDensity; float sunX, sunY, sunZ; };
+
+template <class DAG>
+__global__ void __launch_bounds__(kBlockThreads) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
+                                                                      const PixelMap map, const uint4* __restrict__ paths, u32* __restrict__ colors)
+{
+    u32 x, y;
+    if (!thread_pixel(map, x, y)) return;
+    const u64 idx = map.index(x, y);
+    const uint4 p = paths[idx];
+
+    double dirx, diry, dirz;
+    primary_direction(cam, x, map.height - 1 - y, dirx, diry, dirz);   // the row flip of tracer.cu:622 cancels the one of :251
+
+    // setColor (tracer.cu:604-619) + applyFog (:551-572); contraction as in the reference PTX
+    const float fd = __fmul_rn(sp.fogDensity, 0.00001f);
+    auto shade = [&](float lightScale, double distance, double rdx, double rdy, double rdz) {
+        const float3 c = rgb888_to_float3(colors[idx]);
+        const float lx = __fmul_rn(c.x, lightScale), ly = __fmul_rn(c.y, lightScale), lz = __fmul_rn(c.z, lightScale);
+        const double fogAmount = __dsub_rn(1.0, exp(__dmul_rn(-distance, double(fd))));
+        const double dotp = __fma_rn(rdz, double(sp.sunZ), __fma_rn(rdx, double(sp.sunX), __dmul_rn(rdy, double(sp.sunY))));
+        const double sunAmount = __dmul_rn(double(1.01f), fmax(dotp, 0.0));
+        const float pw = __double2float_rn(pow(sunAmount, 30.0)), q = __fsub_rn(1.f, pw);
+        const float fx = __fmaf_rn(q, __fdiv_rn(187.f, 255.f), pw), fy = __fmaf_rn(q, __fdiv_rn(242.f, 255.f), pw), fz = __fmaf_rn(q, __fdiv_rn(250.f, 255.f), pw);
+        const float g = clampf(__double2float_rn(fogAmount), 0.f, 1.f), h = __fsub_rn(1.f, g);
+        colors[idx] = float3_to_rgb888(__fmaf_rn(lx, h, __fmul_rn(g, fx)), __fmaf_rn(ly, h, __fmul_rn(g, fy)), __fmaf_rn(lz, h, __fmul_rn(g, fz)));
+    };
+    if ((p.x | p.y | p.z) == 0) { shade(1.0f, 1e9, dirx, diry, dirz); return; }
+
+    // ray_box_intersection (tracer.cu:574-587) against the voxel [p, p+1]
+    const double bo[3] = { double(__uint2float_rn(p.x)), double(__uint2float_rn(p.y)), double(__uint2float_rn(p.z)) };
+    const double dv[3] = { dirx, diry, dirz };
+    double rm[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double t0 = __ddiv_rn(__dsub_rn(bo[k], cam.cam[k]), dv[k]);
+        const double t1 = __ddiv_rn(__dsub_rn(__dadd_rn(bo[k], 1.0), cam.cam[k]), dv[k]);
+        rm[k] = (t0 < t1) ? t0 : t1;
+    }
+    const double maxmin = fmax(fmax(rm[0], rm[1]), rm[2]);
+    Ray ray;
+    ray.ox = __fmaf_rn(sp.shadowBias, sp.sunX, __double2float_rn(__fma_rn(dv[0], maxmin, cam.cam[0])));
+    ray.oy = __fmaf_rn(sp.shadowBias, sp.sunY, __double2float_rn(__fma_rn(dv[1], maxmin, cam.cam[1])));
+    ray.oz = __fmaf_rn(sp.shadowBias, sp.sunZ, __double2float_rn(__fma_rn(dv[2], maxmin, cam.cam[2])));
+    ray.dx = sp.sunX; ray.dy = sp.sunY; ray.dz = sp.sunZ;
+    ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
+    u32 hx, hy, hz;
+    const bool shadowed = traverse<DAG, false>(dag, levels, ray, nullptr, 0, hx, hy, hz);
+
+    const double vx = __dsub_rn(bo[0], cam.cam[0]), vy = __dsub_rn(bo[1], cam.cam[1]), vz = __dsub_rn(bo[2], cam.cam[2]);
+    const double dist = __dsqrt_rn(__fma_rn(vz, vz, __fma_rn(vx, vx, __dmul_rn(vy, vy))));
+    shade(shadowed ? 0.5f : 1.0f, dist, __ddiv_rn(vx, dist), __ddiv_rn(vy, dist), __ddiv_rn(vz, dist));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small plumbing kernels
+// ---------------------------------------------------------------------------------------------
+// Scatter compact per-rank tile buffers (world of them, each maxTiles tiles) into a row-major frame.
+template <class T>
+__global__ void assemble_kernel(const T* __restrict__ gathered, T* __restrict__ frame, PixelMap map, u64 tilePixelsPerRank)
+{
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= map.width || y >= map.height) return;
+    const u32 t = (y >> map.tileLog2) * map.tilesX + (x >> map.tileLog2);
+    PixelMap m = map;
+    m.world = map.world; m.rank = t % map.world;
+    const u64 src = u64(t % map.world) * tilePixelsPerRank + (map.world == 1 ? (u64(y) * map.width + x) : m.index(x, y));
+    frame[u64(y) * map.width + x] = gathered[src];
+}
+
+// Copy this rank's compact buffer into a row-major frame, leaving other ranks' pixels untouched.
+template <class T>
+__global__ void untile_own_kernel(const T* __restrict__ compact, T* __restrict__ frame, PixelMap map)
+{
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= map.width || y >= map.height) return;
+    const u32 t = (y >> map.tileLog2) * map.tilesX + (x >> map.tileLog2);
+    if (t % map.world != map.rank) return;
+    frame[u64(y) * map.width + x] = compact[map.index(x, y)];
+}
+
+__global__ void count_hits_kernel(const uint4* __restrict__ paths, u64 n, unsigned long long* __restrict__ out)
+{
+    u32 local = 0;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += u64(gridDim.x) * blockDim.x) {
+        const uint4 p = paths[i];
+        local += (p.x | p.y | p.z) != 0;
+    }
+    local = __reduce_add_sync(0xFFFFFFFFu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
+__global__ void apply_ranges_kernel(u32* __restrict__ dst, const u32* __restrict__ payload, const hdt_range* __restrict__ ranges, u32 nRanges)
+{
+    // one CTA per range, coalesced copy
+    for (u32 r = blockIdx.x; r < nRanges; r += gridDim.x) {
+        const hdt_range rg = ranges[r];
+        for (u64 i = threadIdx.x; i < rg.n_words; i += blockDim.x) dst[rg.dst_word + i] = payload[rg.src_word + i];
+    }
+}
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char* what)
+{
+    g_lastError = what;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where)
+{
+    g_lastError = std::string(where) + ": " + cudaGetErrorString(e);
+    return HDT_ERR_CUDA + int(e);
+}
+#define HDT_CUDA(call)                                          \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+    } while (0)
+
+}  // namespace
+
+struct hdt_ctx {
+    int device = 0;
+    u32 levels = 0;
+    PixelMap map{};
+    u32 nOwnedTiles = 0, maxTilesPerRank = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {};
+    cudaEvent_t timer[2] = {};
+    unsigned long long* hitCounter = nullptr;  // device
+    uint4* paths = nullptr;      // compact (tiled) when world > 1, row-major otherwise
+    u32* colors = nullptr;
+    uint4* framePaths = nullptr; // row-major staging for read-back / assembly when world > 1
+    u32* frameColors = nullptr;
+    u32* pathCache = nullptr;    // pinned, 4 words
+    u64 launches = 0;
+
+    u64 buffer_pixels() const { return map.world == 1 ? u64(map.width) * map.height : (u64(maxTilesPerRank) << (2 * map.tileLog2)); }
+    u32 grid_blocks() const
+    {
+        const u32 T = 1u << map.tileLog2;
+        return nOwnedTiles * (T / kBlockW) * (T / kBlockH);
+    }
+};
+
+namespace {
+
+int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
+{
+    if (world == 0 || rank >= world || tileLog2 < 5 || tileLog2 > 10) return fail(HDT_ERR_ARG, "bad partition");
+    HDT_CUDA(cudaSetDevice(c->device));
+    if (c->paths) { cudaFree(c->paths); c->paths = nullptr; }
+    if (c->colors) { cudaFree(c->colors); c->colors = nullptr; }
+    if (c->framePaths) { cudaFree(c->framePaths); c->framePaths = nullptr; }
+    if (c->frameColors) { cudaFree(c->frameColors); c->frameColors = nullptr; }
+    PixelMap& m = c->map;
+    m.tileLog2 = tileLog2; m.world = world; m.rank = rank;
+    const u32 T = 1u << tileLog2;
+    m.tilesX = (m.width + T - 1) / T; m.tilesY = (m.height + T - 1) / T;
+    const u32 nTiles = m.tilesX * m.tilesY;
+    c->nOwnedTiles = (nTiles > rank) ? (nTiles - rank + world - 1) / world : 0;
+    c->maxTilesPerRank = (nTiles + world - 1) / world;
+    const u64 n = c->buffer_pixels();
+    HDT_CUDA(cudaMalloc(&c->paths, n * sizeof(uint4)));
+    HDT_CUDA(cudaMalloc(&c->colors, n * sizeof(u32)));
+    HDT_CUDA(cudaMemsetAsync(c->paths, 0, n * sizeof(uint4), c->stream));
+    HDT_CUDA(cudaMemsetAsync(c->colors, 0, n * sizeof(u32), c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    return HDT_OK;
+}
+
+struct DagArg { int kind; BasicDagDev basic; HashDagDev hash; };
+
+int parse_dag(int kind, const void* pod, size_t size, DagArg& out)
+{
+    if (!pod) return fail(HDT_ERR_ARG, "null DAG");
+    out.kind = kind;
+    if (kind == HDT_DAG_BASIC) {
+        if (size != sizeof(hdt_basic_dag)) return fail(HDT_ERR_POD_SIZE, "BasicDAG: expected 16 bytes");
+        hdt_basic_dag d; memcpy(&d, pod, sizeof(d));
+        if (!d.data.data) return fail(HDT_ERR_ARG, "BasicDAG: null data");
+        out.basic.data = static_cast<const u32*>(d.data.data);
+        return HDT_OK;
+    }
+    if (kind == HDT_DAG_HASH) {
+        if (size != sizeof(hdt_hash_dag)) return fail(HDT_ERR_POD_SIZE, "HashDAG: expected 32 bytes");
+        hdt_hash_dag d; memcpy(&d, pod, sizeof(d));
+        if (!d.pool || !d.page_table) return fail(HDT_ERR_ARG, "HashDAG: null pool / page table");
+        if (u64(d.pool_top) * kPageWords > (u64(1) << 32)) return fail(HDT_ERR_ARG, "HashDAG: pool beyond 2^32 words");
+        out.hash.pool = d.pool; out.hash.pageTable = d.page_table; out.hash.firstNodeIndex = d.first_node_index;
+        return HDT_OK;
+    }
+    return fail(HDT_ERR_ARG, "unknown DAG kind");
+}
+
+ColorLeafDev leaf_dev(const hdt_color_leaf& l)
+{
+    ColorLeafDev d;
+    d.offset = l.offset;
+    d.weights = static_cast<const u32*>(l.weights_gpu.data); d.nWeights = l.weights_gpu.size;
+    d.blocks = static_cast<const u64*>(l.blocks_gpu.data); d.nBlocks = l.blocks_gpu.size;
+    d.macroBlocks = static_cast<const u64*>(l.macro_blocks_gpu.data); d.nMacroWords = l.macro_blocks_gpu.size;
+    return d;
+}
+
+int parse_colors(int kind, const void* pod, size_t size, ColorsDev& out)
+{
+    if (!pod) return fail(HDT_ERR_ARG, "null colours");
+    memset(&out, 0, sizeof(out));
+    out.kind = kind;
+    switch (kind) {
+    case HDT_COLORS_COMPRESSED: {
+        if (size != sizeof(hdt_basic_compressed_colors)) return fail(HDT_ERR_POD_SIZE, "BasicDAGCompressedColors: expected 128 bytes");
+        hdt_basic_compressed_colors c; memcpy(&c, pod, sizeof(c));
+        out.topLevels = c.base.top_levels; out.enclosedLeaves = static_cast<const u64*>(c.base.enclosed_leaves.data);
+        out.leaf = leaf_dev(c.leaf);
+        return HDT_OK;
+    }
+    case HDT_COLORS_UNCOMPRESSED: {
+        if (size != sizeof(hdt_basic_uncompressed_colors)) return fail(HDT_ERR_POD_SIZE, "BasicDAGUncompressedColors: expected 40 bytes");
+        hdt_basic_uncompressed_colors c; memcpy(&c, pod, sizeof(c));
+        out.topLevels = c.base.top_levels; out.enclosedLeaves = static_cast<const u64*>(c.base.enclosed_leaves.data);
+        out.uncompressed = static_cast<const u32*>(c.colors.data); out.nUncompressed = c.colors.size;
+        return HDT_OK;
+    }
+    case HDT_COLORS_ERRORS: {
+        if (size != sizeof(hdt_basic_color_errors)) return fail(HDT_ERR_POD_SIZE, "BasicDAGColorErrors: expected 288 bytes");
+        hdt_basic_color_errors c; memcpy(&c, pod, sizeof(c));
+        out.topLevels = c.compressed.base.top_levels; out.enclosedLeaves = static_cast<const u64*>(c.compressed.base.enclosed_leaves.data);
+        out.leaf = leaf_dev(c.compressed.leaf);
+        out.uncompressed = static_cast<const u32*>(c.uncompressed.colors.data); out.nUncompressed = c.uncompressed.colors.size;
+        return HDT_OK;
+    }
+    case HDT_COLORS_HASH: {
+        if (size != sizeof(hdt_hash_colors)) return fail(HDT_ERR_POD_SIZE, "HashDAGColors: expected 248 bytes");
+        hdt_hash_colors c; memcpy(&c, pod, sizeof(c));
+        if (!c.nodes_gpu.data) return fail(HDT_ERR_ARG, "HashDAGColors: null nodes");
+        out.nodes = static_cast<const u32*>(c.nodes_gpu.data);
+        out.leaves = static_cast<const ColorLeafPod*>(c.leaves_gpu.data);
+        out.offsets = static_cast<const u64*>(c.offsets_gpu.data);
+        out.leaf = leaf_dev(c.main_leaf);
+        return HDT_OK;
+    }
+    }
+    return fail(HDT_ERR_ARG, "unknown colours kind");
+}
+
+CameraParams make_cam(const double cam[3], const double rmin[3], const double ddx[3], const double ddy[3])
+{
+    CameraParams p;
+    for (int k = 0; k < 3; ++k) { p.cam[k] = cam[k]; p.rayMin[k] = rmin[k]; p.ddx[k] = ddx[k]; p.ddy[k] = ddy[k]; }
+    return p;
+}
+
+ShadowParams make_shadow(float bias, float fog)
+{
+    // sun_direction(), tracer.cu:546-549: normalize(float3(0.3, 1, 0.5)) in IEEE single without
+    // contraction -- the same values the reference compiler folded into its SASS immediates.
+    volatile float x = 0.3f, y = 1.f, z = 0.5f;
+    volatile float xx = x * x, yy = y * y, zz = z * z;
+    volatile float s1 = xx + yy;
+    volatile float s2 = s1 + zz;
+    const float len = sqrtf(s2);
+    volatile float r = 1.0f / len;
+    ShadowParams sp;
+    sp.shadowBias = bias; sp.fogDensity = fog;
+    volatile float sx = r * x, sy = r * y, sz = r * z;
+    sp.sunX = sx; sp.sunY = sy; sp.sunZ = sz;
+    return sp;
+}
+
+void launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
+{
+    const dim3 grid(c->grid_blocks()), block(kBlockThreads);
+    if (!grid.x) return;
+    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->paths);
+    else trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->paths);
+    ++c->launches;
+}
+void launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const ColorsParams& prm)
+{
+    const dim3 grid(c->grid_blocks()), block(kBlockThreads);
+    if (!grid.x) return;
+    if (d.kind == HDT_DAG_BASIC) trace_colors_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(d.basic, col, c->levels, prm, c->map, c->paths, c->colors);
+    else trace_colors_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(d.hash, col, c->levels, prm, c->map, c->paths, c->colors);
+    ++c->launches;
+}
+void launch_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp)
+{
+    const dim3 grid(c->grid_blocks()), block(kBlockThreads);
+    if (!grid.x) return;
+    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->colors);
+    else trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->colors);
+    ++c->launches;
+}
+
+int check_combo(int dagKind, int colorsKind)
+{
+    // the instantiations the reference provides (tracer.cu:705-711)
+    if ((dagKind == HDT_DAG_HASH) != (colorsKind == HDT_COLORS_HASH)) return fail(HDT_ERR_ARG, "DAG / colours combination not provided by the tracer");
+    return HDT_OK;
+}
+
+int finish_timed(hdt_ctx* c, cudaEvent_t a, cudaEvent_t b, float* ms)
+{
+    HDT_CUDA(cudaEventSynchronize(b));
+    HDT_CUDA(cudaGetLastError());
+    if (ms) HDT_CUDA(cudaEventElapsedTime(ms, a, b));
+    return HDT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hdt_last_error(void) { return g_lastError.c_str(); }
+int hdt_version(void) { return 1; }
+uint64_t hdt_launch_count(const hdt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt_ctx** out)
+{
+    if (!out || !width || !height) return fail(HDT_ERR_ARG, "hdt_create: bad arguments");
+    if (levels < 3 || levels > kMaxLevels) return fail(HDT_ERR_ARG, "hdt_create: levels must be in [3, 24]");
+    int n = 0;
+    HDT_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(HDT_ERR_ARG, "hdt_create: no such CUDA device");
+    HDT_CUDA(cudaSetDevice(device));
+    hdt_ctx* c = new hdt_ctx();
+    c->device = device; c->levels = levels;
+    c->map.width = width; c->map.height = height;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->timer[i]);
+    if (e == cudaSuccess) e = cudaMalloc(&c->hitCounter, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->pathCache, 4 * sizeof(u32));
+    if (e != cudaSuccess) { hdt_destroy(c); return cuda_fail(e, "hdt_create"); }
+    const int rc = configure(c, 0, 1, 6);
+    if (rc) { hdt_destroy(c); return rc; }
+    *out = c;
+    return HDT_OK;
+}
+
+int hdt_destroy(hdt_ctx* c)
+{
+    if (!c) return HDT_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->paths); cudaFree(c->colors); cudaFree(c->framePaths); cudaFree(c->frameColors);
+    if (c->pathCache) cudaFreeHost(c->pathCache);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->timer) if (e) cudaEventDestroy(e);
+    cudaFree(c->hitCounter);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return HDT_OK;
+}
+
+int hdt_set_partition(hdt_ctx* c, uint32_t rank, uint32_t world, uint32_t tile_log2)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    return configure(c, rank, world, tile_log2);
+}
+
+int hdt_resolve_paths(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, const double cam[3], const double ray_min[3],
+                      const double ray_ddx[3], const double ray_ddy[3], float* ms)
+{
+    if (!c || !cam || !ray_min || !ray_ddx || !ray_ddy) return fail(HDT_ERR_ARG, "hdt_resolve_paths: null argument");
+    DagArg d;
+    if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, d)) return rc;
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    launch_paths(c, d, make_cam(cam, ray_min, ray_ddx, ray_ddy));
+    HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    return finish_timed(c, c->ev[0], c->ev[1], ms);
+}
+
+int hdt_resolve_colors(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, int colors_kind, const void* colors_pod,
+                       size_t colors_pod_size, int debug_colors, uint32_t debug_level, const hdt_tool_info* tool, int overlay, float* ms)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    if (debug_colors < 0 || debug_colors > HDT_DEBUG_WEIGHT) return fail(HDT_ERR_ARG, "unknown debug colour mode");
+    DagArg d; ColorsDev col;
+    if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, d)) return rc;
+    if (int rc = parse_colors(colors_kind, colors_pod, colors_pod_size, col)) return rc;
+    if (int rc = check_combo(dag_kind, colors_kind)) return rc;
+    ColorsParams prm{};
+    prm.debugColors = debug_colors; prm.debugIndexLevel = debug_level; prm.overlay = (overlay && tool) ? 1 : 0;
+    if (tool) prm.tool = *tool;
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    launch_colors(c, d, col, prm);
+    HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    return finish_timed(c, c->ev[0], c->ev[1], ms);
+}
+
+int hdt_resolve_shadows(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, const double cam[3], const double ray_min[3],
+                        const double ray_ddx[3], const double ray_ddy[3], float shadow_bias, float fog_density, float* ms)
+{
+    if (!c || !cam || !ray_min || !ray_ddx || !ray_ddy) return fail(HDT_ERR_ARG, "hdt_resolve_shadows: null argument");
+    DagArg d;
+    if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, d)) return rc;
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    launch_shadows(c, d, make_cam(cam, ray_min, ray_ddx, ray_ddy), make_shadow(shadow_bias, fog_density));
+    HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    return finish_timed(c, c->ev[0], c->ev[1], ms);
+}
+
+static int enqueue_frame(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, int colors_kind, const void* colors_pod,
+                         size_t colors_pod_size, const double cam[3], const double ray_min[3], const double ray_ddx[3], const double ray_ddy[3],
+                         float shadow_bias, float fog_density, int with_shadows, uint32_t* host_colors, bool events)
+{
+    if (!c || !cam || !ray_min || !ray_ddx || !ray_ddy) return fail(HDT_ERR_ARG, "hdt_resolve_frame: null argument");
+    DagArg d; ColorsDev col;
+    if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, d)) return rc;
+    if (int rc = parse_colors(colors_kind, colors_pod, colors_pod_size, col)) return rc;
+    if (int rc = check_combo(dag_kind, colors_kind)) return rc;
+    if (host_colors && c->map.world != 1) return fail(HDT_ERR_STATE, "hdt_resolve_frame: host read-back needs an unpartitioned context");
+    const CameraParams cp = make_cam(cam, ray_min, ray_ddx, ray_ddy);
+    ColorsParams prm{};
+    HDT_CUDA(cudaSetDevice(c->device));
+    if (events) HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    launch_paths(c, d, cp);
+    if (events) HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    launch_colors(c, d, col, prm);
+    if (events) HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if (with_shadows) launch_shadows(c, d, cp, make_shadow(shadow_bias, fog_density));
+    if (events) HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    if (host_colors)
+        HDT_CUDA(cudaMemcpyAsync(host_colors, c->colors, u64(c->map.width) * c->map.height * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    return HDT_OK;
+}
+
+int hdt_resolve_frame(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, int colors_kind, const void* colors_pod,
+                      size_t colors_pod_size, const double cam[3], const double ray_min[3], const double ray_ddx[3], const double ray_ddy[3],
+                      float shadow_bias, float fog_density, int with_shadows, uint32_t* host_colors, float ms[3])
+{
+    if (int rc = enqueue_frame(c, dag_kind, dag_pod, dag_pod_size, colors_kind, colors_pod, colors_pod_size, cam, ray_min, ray_ddx, ray_ddy,
+                               shadow_bias, fog_density, with_shadows, host_colors, true)) return rc;
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    if (ms) {
+        HDT_CUDA(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
+        HDT_CUDA(cudaEventElapsedTime(&ms[1], c->ev[1], c->ev[2]));
+        HDT_CUDA(cudaEventElapsedTime(&ms[2], c->ev[2], c->ev[3]));
+    }
+    return HDT_OK;
+}
+
+int hdt_resolve_frame_async(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, int colors_kind, const void* colors_pod,
+                            size_t colors_pod_size, const double cam[3], const double ray_min[3], const double ray_ddx[3], const double ray_ddy[3],
+                            float shadow_bias, float fog_density, int with_shadows, uint32_t* host_colors)
+{
+    return enqueue_frame(c, dag_kind, dag_pod, dag_pod_size, colors_kind, colors_pod, colors_pod_size, cam, ray_min, ray_ddx, ray_ddy,
+                         shadow_bias, fog_density, with_shadows, host_colors, false);
+}
+
+int hdt_sync(hdt_ctx* c)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+int hdt_timer_begin(hdt_ctx* c)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaEventRecord(c->timer[0], c->stream));
+    return HDT_OK;
+}
+
+int hdt_timer_end(hdt_ctx* c, float* ms)
+{
+    if (!c || !ms) return fail(HDT_ERR_ARG, "null argument");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaEventRecord(c->timer[1], c->stream));
+    HDT_CUDA(cudaEventSynchronize(c->timer[1]));
+    HDT_CUDA(cudaGetLastError());
+    HDT_CUDA(cudaEventElapsedTime(ms, c->timer[0], c->timer[1]));
+    return HDT_OK;
+}
+
+int hdt_count_hits(hdt_ctx* c, uint64_t* n_hits)
+{
+    if (!c || !n_hits) return fail(HDT_ERR_ARG, "null argument");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaMemsetAsync(c->hitCounter, 0, sizeof(unsigned long long), c->stream));
+    const u64 n = c->map.world == 1 ? u64(c->map.width) * c->map.height : (u64(c->nOwnedTiles) << (2 * c->map.tileLog2));
+    count_hits_kernel<<<592, 256, 0, c->stream>>>(c->paths, n, c->hitCounter);
+    ++c->launches;
+    unsigned long long v = 0;
+    HDT_CUDA(cudaMemcpyAsync(&v, c->hitCounter, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    *n_hits = v;
+    return HDT_OK;
+}
+
+int hdt_get_path(hdt_ctx* c, uint32_t x, uint32_t y, uint32_t out[3])
+{
+    if (!c || !out) return fail(HDT_ERR_ARG, "null argument");
+    if (x >= c->map.width || y >= c->map.height) return fail(HDT_ERR_ARG, "pixel outside the frame");
+    const u32 t = (y >> c->map.tileLog2) * c->map.tilesX + (x >> c->map.tileLog2);
+    if (t % c->map.world != c->map.rank) return fail(HDT_ERR_STATE, "pixel belongs to another rank");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaMemcpyAsync(c->pathCache, c->paths + c->map.index(x, y), sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    out[0] = c->pathCache[0]; out[1] = c->pathCache[1]; out[2] = c->pathCache[2];
+    return HDT_OK;
+}
+
+static int read_frame(hdt_ctx* c, bool paths, void* host)
+{
+    if (!c || !host) return fail(HDT_ERR_ARG, "null argument");
+    HDT_CUDA(cudaSetDevice(c->device));
+    const u64 n = u64(c->map.width) * c->map.height;
+    if (c->map.world == 1) {
+        if (paths) HDT_CUDA(cudaMemcpyAsync(host, c->paths, n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+        else HDT_CUDA(cudaMemcpyAsync(host, c->colors, n * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+        HDT_CUDA(cudaStreamSynchronize(c->stream));
+        return HDT_OK;
+    }
+    const dim3 block(32, 8), grid((c->map.width + 31) / 32, (c->map.height + 7) / 8);
+    if (paths) {
+        if (!c->framePaths) HDT_CUDA(cudaMalloc(&c->framePaths, n * sizeof(uint4)));
+        HDT_CUDA(cudaMemsetAsync(c->framePaths, 0, n * sizeof(uint4), c->stream));
+        untile_own_kernel<uint4><<<grid, block, 0, c->stream>>>(c->paths, c->framePaths, c->map);
+        HDT_CUDA(cudaMemcpyAsync(host, c->framePaths, n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        if (!c->frameColors) HDT_CUDA(cudaMalloc(&c->frameColors, n * sizeof(u32)));
+        HDT_CUDA(cudaMemsetAsync(c->frameColors, 0, n * sizeof(u32), c->stream));
+        untile_own_kernel<u32><<<grid, block, 0, c->stream>>>(c->colors, c->frameColors, c->map);
+        HDT_CUDA(cudaMemcpyAsync(host, c->frameColors, n * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ++c->launches;
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+int hdt_read_paths(hdt_ctx* c, uint32_t* host) { return read_frame(c, true, host); }
+int hdt_read_colors(hdt_ctx* c, uint32_t* host) { return read_frame(c, false, host); }
+
+int hdt_partition_buffers(hdt_ctx* c, void** paths_dev, void** colors_dev, uint64_t* n_owned, uint64_t* max_tiles)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    if (paths_dev) *paths_dev = c->paths;
+    if (colors_dev) *colors_dev = c->colors;
+    if (n_owned) *n_owned = c->nOwnedTiles;
+    if (max_tiles) *max_tiles = c->map.world == 1 ? 0 : c->maxTilesPerRank;
+    return HDT_OK;
+}
+
+int hdt_assemble_colors(hdt_ctx* c, const uint32_t* gathered_dev, uint32_t* frame_dev)
+{
+    if (!c || !gathered_dev) return fail(HDT_ERR_ARG, "null argument");
+    HDT_CUDA(cudaSetDevice(c->device));
+    const u64 n = u64(c->map.width) * c->map.height;
+    if (!frame_dev) {
+        if (!c->frameColors) HDT_CUDA(cudaMalloc(&c->frameColors, n * sizeof(u32)));
+        frame_dev = c->frameColors;
+    }
+    const dim3 block(32, 8), grid((c->map.width + 31) / 32, (c->map.height + 7) / 8);
+    assemble_kernel<u32><<<grid, block, 0, c->stream>>>(gathered_dev, frame_dev, c->map, c->buffer_pixels());
+    ++c->launches;
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+int hdt_apply_ranges(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload_dev, const hdt_range* ranges_dev, uint32_t n_ranges)
+{
+    if (!c || !dst_dev || !payload_dev || (!ranges_dev && n_ranges)) return fail(HDT_ERR_ARG, "null argument");
+    if (!n_ranges) return HDT_OK;
+    HDT_CUDA(cudaSetDevice(c->device));
+    apply_ranges_kernel<<<n_ranges < 1184 ? n_ranges : 1184, 128, 0, c->stream>>>(dst_dev, payload_dev, ranges_dev, n_ranges);
+    ++c->launches;
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,365 @@
+"""Host-side mirror of the reference's tracer interface over the C ABI (include/hashdag_b200.h).
+
+`DAGTracer` keeps the reference class's methods and argument meaning
+(/root/reference/src/dag_tracer.h:9-43): resolve_paths / resolve_colors / resolve_shadows return the
+kernel time in milliseconds, get_path returns the voxel under a pixel.  The DAG and colour classes
+are the device-resident counterparts of BasicDAG (basic_dag.h:11-45), HashDAG (hash_dag.h:214-253),
+BasicDAG*Colors (basic_dag.h:47-242) and HashDAGColors (hash_dag_colors.h:9-73); each produces the
+bytes the reference would pass to its kernels by value.
+
+PyTorch is used for device memory only.  There is no CPU path: without libhashdag_b200.so or
+without a CUDA device every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+from .camera import CameraView, DAGInfo, trace_params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhashdag_b200.so")
+
+DAG_BASIC, DAG_HASH = 0, 1
+COLORS_UNCOMPRESSED, COLORS_COMPRESSED, COLORS_ERRORS, COLORS_HASH = 0, 1, 2, 3
+UNIQUE_OFFSET = 0xFFFFFFFFFFFFFFFF
+
+# EDebugColors, tracer.h:7-17
+DEBUG_NONE, DEBUG_INDEX, DEBUG_POSITION, DEBUG_COLOR_TREE, DEBUG_COLOR_BITS, DEBUG_MIN_COLOR, DEBUG_MAX_COLOR, DEBUG_WEIGHT = range(8)
+
+EXPORTS = (
+    "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_resolve_paths", "hdt_resolve_colors",
+    "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
+    "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
+    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_apply_ranges", "hdt_launch_count", "hdt_version",
+)
+
+
+class TracerError(RuntimeError):
+    pass
+
+
+class ToolInfo(C.Structure):  # tracer.h:33-39
+    _fields_ = [("tool", C.c_int32), ("position", C.c_uint32 * 3), ("radius", C.c_float),
+                ("copy_source", C.c_uint32 * 3), ("copy_dest", C.c_uint32 * 3)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libhashdag_b200.so; raises TracerError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TracerError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    d3 = C.POINTER(C.c_double)
+    fp = C.POINTER(C.c_float)
+    lib.hdt_last_error.restype = C.c_char_p
+    lib.hdt_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+    lib.hdt_destroy.argtypes = [C.c_void_p]
+    lib.hdt_set_partition.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.hdt_resolve_paths.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, d3, d3, d3, d3, fp]
+    lib.hdt_resolve_colors.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32,
+                                       C.POINTER(ToolInfo), C.c_int, fp]
+    lib.hdt_resolve_shadows.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, d3, d3, d3, d3, C.c_float, C.c_float, fp]
+    lib.hdt_resolve_frame.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, d3, d3, d3, d3,
+                                      C.c_float, C.c_float, C.c_int, C.c_void_p, fp]
+    lib.hdt_resolve_frame_async.argtypes = lib.hdt_resolve_frame.argtypes[:-1]
+    lib.hdt_sync.argtypes = [C.c_void_p]
+    lib.hdt_timer_begin.argtypes = [C.c_void_p]
+    lib.hdt_timer_end.argtypes = [C.c_void_p, fp]
+    lib.hdt_count_hits.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.hdt_get_path.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.hdt_read_paths.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hdt_read_colors.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hdt_partition_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.hdt_assemble_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hdt_apply_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.hdt_launch_count.restype = C.c_uint64
+    lib.hdt_launch_count.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise TracerError(f"hashdag_b200 error {rc}: {load_library().hdt_last_error().decode()}")
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise TracerError("hashdag_b200 needs a CUDA device (there is no CPU path)")
+    return torch
+
+
+def _to_device(arr: np.ndarray, device):
+    """numpy (uint32/uint64) -> device tensor with the same bytes."""
+    torch = _torch()
+    if arr is None or arr.size == 0:
+        return None
+    view = {4: np.int32, 8: np.int64}[arr.dtype.itemsize]
+    return torch.from_numpy(np.ascontiguousarray(arr).view(view)).to(device)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _n(t):
+    return 0 if t is None else t.numel()
+
+
+def _array(t):        # StaticArray<T>
+    return struct.pack("<QQ", _ptr(t), _n(t))
+
+
+def _dyn_array(t):    # DynamicArray<T>
+    return struct.pack("<QQQ", _ptr(t), _n(t), _n(t))
+
+
+_NULL_ARRAY = struct.pack("<QQ", 0, 0)
+_NULL_DYN = struct.pack("<QQQ", 0, 0, 0)
+
+
+class BasicDAG:
+    """Device-resident BasicDAG (basic_dag.h:11-45): one uint32 array, root at word 0."""
+    kind = DAG_BASIC
+
+    def __init__(self, data_tensor, levels):
+        self.data, self.levels = data_tensor, levels
+
+    @classmethod
+    def from_scene(cls, scene, device="cuda:0"):
+        return cls(_to_device(scene.basic, device), scene.levels)
+
+    def pod(self) -> bytes:
+        return _array(self.data)
+
+
+class HashDAG:
+    """Device-resident HashDAG read side (hash_dag.h:214-253, hash_table.h:818-826)."""
+    kind = DAG_HASH
+
+    def __init__(self, pool, page_table, pool_top, first_node_index, levels):
+        self.pool, self.page_table = pool, page_table
+        self.pool_top, self.first_node_index, self.levels = pool_top, first_node_index, levels
+
+    @classmethod
+    def from_scene(cls, scene, device="cuda:0"):
+        if not scene.has_hash:
+            raise TracerError("scene was built without a HashDAG")
+        return cls(_to_device(scene.hash_pool, device), _to_device(scene.hash_page_table, device),
+                   scene.hash_pool_top, scene.hash_first_node_index, scene.levels)
+
+    def pod(self) -> bytes:
+        return struct.pack("<IIQQII", _n(self.page_table), self.pool_top, _ptr(self.page_table), _ptr(self.pool), self.first_node_index, 0)
+
+
+class CompressedColorLeaf:
+    """CompressedColorLeaf (vwsc.h:157-191), GPU arrays only."""
+
+    def __init__(self, weights, blocks, macro_blocks, offset=UNIQUE_OFFSET):
+        self.weights, self.blocks, self.macro_blocks, self.offset = weights, blocks, macro_blocks, offset
+
+    @classmethod
+    def from_scene(cls, scene, device="cuda:0"):
+        return cls(_to_device(scene.weights, device), _to_device(scene.blocks, device), _to_device(scene.macro_blocks, device), UNIQUE_OFFSET)
+
+    def pod(self) -> bytes:
+        return struct.pack("<Q", self.offset) + _array(self.weights) + _array(self.blocks) + _array(self.macro_blocks) + 3 * _NULL_ARRAY
+
+
+class _BasicColorsBase:
+    def __init__(self, top_levels, enclosed_leaves):
+        self.top_levels, self.enclosed_leaves = top_levels, enclosed_leaves
+
+    def _base_pod(self) -> bytes:
+        return struct.pack("<II", self.top_levels, 0) + _array(self.enclosed_leaves)
+
+
+class BasicDAGCompressedColors(_BasicColorsBase):
+    kind = COLORS_COMPRESSED
+
+    def __init__(self, top_levels, enclosed_leaves, leaf):
+        super().__init__(top_levels, enclosed_leaves)
+        self.leaf = leaf
+
+    @classmethod
+    def from_scene(cls, scene, device="cuda:0"):
+        return cls(scene.top_levels, _to_device(scene.enclosed_leaves, device), CompressedColorLeaf.from_scene(scene, device))
+
+    def pod(self) -> bytes:
+        return self._base_pod() + self.leaf.pod()
+
+
+class BasicDAGUncompressedColors(_BasicColorsBase):
+    kind = COLORS_UNCOMPRESSED
+
+    def __init__(self, top_levels, enclosed_leaves, colors):
+        super().__init__(top_levels, enclosed_leaves)
+        self.colors = colors
+
+    @classmethod
+    def from_scene(cls, scene, device="cuda:0"):
+        if scene.uncompressed is None:
+            raise TracerError("scene was built without uncompressed colours")
+        return cls(scene.top_levels, _to_device(scene.enclosed_leaves, device), _to_device(scene.uncompressed, device))
+
+    def pod(self) -> bytes:
+        return self._base_pod() + _array(self.colors)
+
+
+class BasicDAGColorErrors:
+    kind = COLORS_ERRORS
+
+    def __init__(self, compressed: BasicDAGCompressedColors, uncompressed: BasicDAGUncompressedColors):
+        self.compressed, self.uncompressed = compressed, uncompressed
+
+    def pod(self) -> bytes:
+        unused_leaf = struct.pack("<Q", 0) + 6 * _NULL_ARRAY + _NULL_ARRAY
+        return unused_leaf + self.compressed.pod() + self.uncompressed.pod()
+
+
+class HashDAGColors:
+    kind = COLORS_HASH
+
+    def __init__(self, nodes, offsets, main_leaf, leaves=None):
+        self.nodes, self.offsets, self.main_leaf, self.leaves = nodes, offsets, main_leaf, leaves
+
+    @classmethod
+    def from_scene(cls, scene, device="cuda:0"):
+        if not scene.has_hash_colors:
+            raise TracerError("HashDAGColors need levels-2 > 10 (hash_dag_factory.cpp:113)")
+        return cls(_to_device(scene.color_nodes, device), _to_device(scene.color_offsets, device), CompressedColorLeaf.from_scene(scene, device))
+
+    def pod(self) -> bytes:
+        leaves = _NULL_DYN if self.leaves is None else struct.pack("<QQQ", _ptr(self.leaves), _n(self.leaves) // 13, _n(self.leaves) // 13)
+        return _dyn_array(self.nodes) + leaves + _dyn_array(self.offsets) + self.main_leaf.pod() + 3 * _NULL_DYN
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+class DAGTracer:
+    """Mirror of the reference's DAGTracer over libhashdag_b200.so.
+
+    Width, height and DAG depth are runtime values (compile-time constants in the reference,
+    typedefs.h:517,683-684).  `head_less` is accepted for signature compatibility; there is no GL path.
+    """
+
+    def __init__(self, head_less: bool = True, width: int = 1920, height: int = 1080, levels: int = 17, device: int = 0):
+        _torch()
+        self._lib = load_library()
+        self.head_less, self.width, self.height, self.levels, self.device = head_less, width, height, levels, device
+        self._ctx = C.c_void_p()
+        _check(self._lib.hdt_create(width, height, levels, device, C.byref(self._ctx)))
+        self._ms = C.c_float()
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.hdt_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _params(self, camera: CameraView, dag_info: DAGInfo):
+        return trace_params(camera, dag_info, self.levels, self.width, self.height)
+
+    # -- the three passes -----------------------------------------------------------------
+    def resolve_paths(self, camera: CameraView, dag_info: DAGInfo, dag) -> float:
+        cam, rmin, ddx, ddy = self._params(camera, dag_info)
+        pod = dag.pod()
+        _check(self._lib.hdt_resolve_paths(self._ctx, dag.kind, pod, len(pod), _d3(cam), _d3(rmin), _d3(ddx), _d3(ddy), C.byref(self._ms)))
+        return self._ms.value
+
+    def resolve_colors(self, dag, colors, debug_colors: int = DEBUG_NONE, debug_colors_index_level: int = 0,
+                       tool_info: ToolInfo | None = None, tool_overlay: bool = False) -> float:
+        pod, cpod = dag.pod(), colors.pod()
+        _check(self._lib.hdt_resolve_colors(self._ctx, dag.kind, pod, len(pod), colors.kind, cpod, len(cpod), int(debug_colors),
+                                            int(debug_colors_index_level), C.byref(tool_info) if tool_info is not None else None,
+                                            int(tool_overlay), C.byref(self._ms)))
+        return self._ms.value
+
+    def resolve_shadows(self, camera: CameraView, dag_info: DAGInfo, dag, shadow_bias: float = 1.0, fog_density: float = 0.0) -> float:
+        cam, rmin, ddx, ddy = self._params(camera, dag_info)
+        pod = dag.pod()
+        _check(self._lib.hdt_resolve_shadows(self._ctx, dag.kind, pod, len(pod), _d3(cam), _d3(rmin), _d3(ddx), _d3(ddy),
+                                             float(shadow_bias), float(fog_density), C.byref(self._ms)))
+        return self._ms.value
+
+    def resolve_frame(self, camera, dag_info, dag, colors, shadow_bias=1.0, fog_density=0.0, with_shadows=True, host_colors=None):
+        """paths + colours + shadows with one synchronisation; returns the three kernel times (ms)."""
+        cam, rmin, ddx, ddy = self._params(camera, dag_info)
+        pod, cpod = dag.pod(), colors.pod()
+        ms = (C.c_float * 3)()
+        host_ptr = None
+        if host_colors is not None:
+            host_ptr = host_colors.data_ptr() if hasattr(host_colors, "data_ptr") else host_colors.ctypes.data
+        _check(self._lib.hdt_resolve_frame(self._ctx, dag.kind, pod, len(pod), colors.kind, cpod, len(cpod), _d3(cam), _d3(rmin), _d3(ddx),
+                                           _d3(ddy), float(shadow_bias), float(fog_density), int(with_shadows), host_ptr, ms))
+        return tuple(ms)
+
+    def enqueue_frame(self, params, dag_pod, dag_kind, colors_pod, colors_kind, shadow_bias=1.0, fog_density=0.0, with_shadows=True, host_ptr=None):
+        """Asynchronous frame from precomputed trace params and POD bytes (bench inner loop)."""
+        cam, rmin, ddx, ddy = params
+        _check(self._lib.hdt_resolve_frame_async(self._ctx, dag_kind, dag_pod, len(dag_pod), colors_kind, colors_pod, len(colors_pod),
+                                                 _d3(cam), _d3(rmin), _d3(ddx), _d3(ddy), float(shadow_bias), float(fog_density),
+                                                 int(with_shadows), host_ptr))
+
+    def sync(self):
+        _check(self._lib.hdt_sync(self._ctx))
+
+    def timer_begin(self):
+        _check(self._lib.hdt_timer_begin(self._ctx))
+
+    def timer_end(self) -> float:
+        _check(self._lib.hdt_timer_end(self._ctx, C.byref(self._ms)))
+        return self._ms.value
+
+    def count_hits(self) -> int:
+        n = C.c_uint64()
+        _check(self._lib.hdt_count_hits(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    def get_path(self, x: int, y: int):
+        out = (C.c_uint32 * 3)()
+        _check(self._lib.hdt_get_path(self._ctx, x, y, out))
+        return tuple(out)
+
+    # -- read-back ------------------------------------------------------------------------
+    def read_paths(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), dtype=np.uint32)
+        _check(self._lib.hdt_read_paths(self._ctx, out.ctypes.data))
+        return out
+
+    def read_colors(self) -> np.ndarray:
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        _check(self._lib.hdt_read_colors(self._ctx, out.ctypes.data))
+        return out
+
+    # -- multi-GPU ------------------------------------------------------------------------
+    def set_partition(self, rank: int, world: int, tile_log2: int = 6):
+        _check(self._lib.hdt_set_partition(self._ctx, rank, world, tile_log2))
+
+    def partition_buffers(self):
+        p, c, n, m = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(self._lib.hdt_partition_buffers(self._ctx, C.byref(p), C.byref(c), C.byref(n), C.byref(m)))
+        return p.value, c.value, n.value, m.value
+
+    def assemble_colors(self, gathered_tensor, frame_tensor=None):
+        _check(self._lib.hdt_assemble_colors(self._ctx, gathered_tensor.data_ptr(), 0 if frame_tensor is None else frame_tensor.data_ptr()))
+
+    def launch_count(self) -> int:
+        return int(self._lib.hdt_launch_count(self._ctx))

@@ -1,0 +1,155 @@
+/* hashdag_b200 -- C ABI of the B200-native DAG tracer.
+ *
+ * Drop-in boundary for the reference's DAGTracer (/root/reference/src/dag_tracer.h:9-43,
+ * dag_tracer.cu:116-256): the C++ shim in hashdag_b200/cpp/dag_tracer_b200.h keeps the
+ * reference's class shape and forwards to these entry points.  Plain pointers and sizes only.
+ *
+ * DAG and colour structures cross the boundary as the reference passes them to its kernels: by
+ * value, as the bytes of the struct (const void* + sizeof).  The hdt_* POD types below mirror the
+ * reference layouts; every entry point checks the size it is handed.
+ *
+ * All functions return 0 on success, a non-zero code otherwise (CUDA errors are returned as
+ * 1000 + cudaError_t); hdt_last_error() describes the last failure on the calling thread.
+ * All resolve_* calls are synchronous like the reference's (dag_tracer.cu:130-133): they return
+ * after the kernel has finished and report its device time in milliseconds.
+ */
+#ifndef HASHDAG_B200_H
+#define HASHDAG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hdt_ctx hdt_ctx;
+
+enum { HDT_DAG_BASIC = 0, HDT_DAG_HASH = 1 };
+enum {
+    HDT_COLORS_UNCOMPRESSED = 0, /* BasicDAGUncompressedColors, basic_dag.h:122-177 */
+    HDT_COLORS_COMPRESSED = 1,   /* BasicDAGCompressedColors,   basic_dag.h:91-120  */
+    HDT_COLORS_ERRORS = 2,       /* BasicDAGColorErrors,        basic_dag.h:179-242 */
+    HDT_COLORS_HASH = 3          /* HashDAGColors,              hash_dag_colors.h:9-73 */
+};
+/* EDebugColors, tracer.h:7-17 */
+enum { HDT_DEBUG_NONE = 0, HDT_DEBUG_INDEX, HDT_DEBUG_POSITION, HDT_DEBUG_COLOR_TREE, HDT_DEBUG_COLOR_BITS,
+       HDT_DEBUG_MIN_COLOR, HDT_DEBUG_MAX_COLOR, HDT_DEBUG_WEIGHT };
+
+enum { HDT_OK = 0, HDT_ERR_ARG = 1, HDT_ERR_POD_SIZE = 2, HDT_ERR_STATE = 3, HDT_ERR_CUDA = 1000 };
+
+/* ---- POD mirrors (device pointers unless the field says _cpu) ------------------------------ */
+typedef struct hdt_array { const void* data; uint64_t size; } hdt_array;                       /* StaticArray<T>,  array.h:8-129  */
+typedef struct hdt_dyn_array { const void* data; uint64_t size; uint64_t allocated; } hdt_dyn_array; /* DynamicArray<T>, array.h:131-227 */
+
+typedef struct hdt_basic_dag { hdt_array data; } hdt_basic_dag;                                /* BasicDAG, basic_dag.h:11-13: 16 B */
+
+typedef struct hdt_hash_dag {                                                                  /* HashDAG, hash_dag.h:214-221 + hash_table.h:818-826: 32 B */
+    uint32_t page_table_size;
+    uint32_t pool_top;
+    const uint32_t* page_table;   /* gpuPageTable */
+    const uint32_t* pool;         /* gpuPool */
+    uint32_t first_node_index;
+    uint32_t _pad;
+} hdt_hash_dag;
+
+typedef struct hdt_color_leaf {                                                                /* CompressedColorLeaf, vwsc.h:157-191: 104 B */
+    uint64_t offset;              /* offset into the shared leaf; UINT64_MAX = unique */
+    hdt_array weights_gpu, blocks_gpu, macro_blocks_gpu;
+    hdt_array weights_cpu, blocks_cpu, macro_blocks_cpu;   /* ignored by the tracer */
+} hdt_color_leaf;
+
+typedef struct hdt_basic_colors_base { uint32_t top_levels; uint32_t _pad; hdt_array enclosed_leaves; } hdt_basic_colors_base; /* basic_dag.h:47-51: 24 B */
+typedef struct hdt_basic_compressed_colors { hdt_basic_colors_base base; hdt_color_leaf leaf; } hdt_basic_compressed_colors;   /* 128 B */
+typedef struct hdt_basic_uncompressed_colors { hdt_basic_colors_base base; hdt_array colors; } hdt_basic_uncompressed_colors;   /* 40 B */
+typedef struct hdt_basic_color_errors {                                                        /* basic_dag.h:179-203: 288 B */
+    hdt_color_leaf leaf_compressed; hdt_array leaf_uncompressed;   /* the unused `leaf` member */
+    hdt_basic_compressed_colors compressed; hdt_basic_uncompressed_colors uncompressed;
+} hdt_basic_color_errors;
+typedef struct hdt_hash_colors {                                                               /* HashDAGColors, hash_dag_colors.h:65-73: 248 B */
+    hdt_dyn_array nodes_gpu, leaves_gpu, offsets_gpu;
+    hdt_color_leaf main_leaf;
+    hdt_dyn_array nodes_cpu, leaves_cpu, offsets_cpu;      /* ignored by the tracer */
+} hdt_hash_colors;
+
+typedef struct hdt_tool_info {                                                                 /* ToolInfo, tracer.h:33-39: 44 B */
+    int32_t tool; uint32_t position[3]; float radius; uint32_t copy_source[3]; uint32_t copy_dest[3];
+} hdt_tool_info;
+
+typedef struct hdt_range { uint64_t dst_word; uint64_t src_word; uint64_t n_words; } hdt_range; /* one dirty span, hash_table.cpp:129-180 */
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Replaces DAGTracer::DAGTracer(headLess=true) (dag_tracer.cu:9-45); width/height/levels are
+ * runtime values here (compile-time imageWidth/imageHeight/MAX_LEVELS in typedefs.h:517,683). */
+int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt_ctx** out);
+int hdt_destroy(hdt_ctx* ctx);                                  /* DAGTracer::~DAGTracer, dag_tracer.cu:48-69 */
+const char* hdt_last_error(void);
+
+/* Screen-space partition for one-process-per-GPU runs: the frame is cut into (1<<tile_log2)^2
+ * pixel tiles, tile t belongs to rank t % world.  Default: rank 0 of 1 (whole frame). */
+int hdt_set_partition(hdt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t tile_log2);
+
+/* ---- the path ------------------------------------------------------------------------------ */
+/* DAGTracer::resolve_paths<TDAG> (dag_tracer.cu:116-143) -> Tracer::trace_paths (tracer.cu:145-252).
+ * cam/ray_min/ray_ddx/ray_ddy are TracePathsParams (tracer.h:81-91), i.e. get_trace_params' output. */
+int hdt_resolve_paths(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size,
+                      const double cam[3], const double ray_min[3], const double ray_ddx[3], const double ray_ddy[3], float* ms);
+
+/* DAGTracer::resolve_colors<TDAG,TDAGColors> (dag_tracer.cu:145-179) -> Tracer::trace_colors
+ * (tracer.cu:254-451).  tool_info may be NULL; tool_overlay mirrors the TOOL_OVERLAY build flag. */
+int hdt_resolve_colors(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size,
+                       int colors_kind, const void* colors_pod, size_t colors_pod_size,
+                       int debug_colors, uint32_t debug_colors_index_level, const hdt_tool_info* tool_info, int tool_overlay, float* ms);
+
+/* DAGTracer::resolve_shadows<TDAG> (dag_tracer.cu:181-219) -> Tracer::trace_shadows (tracer.cu:589-697). */
+int hdt_resolve_shadows(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size,
+                        const double cam[3], const double ray_min[3], const double ray_ddx[3], const double ray_ddy[3],
+                        float shadow_bias, float fog_density, float* ms);
+
+/* One frame = paths + colours + shadows enqueued back to back on the tracer's stream with a single
+ * synchronisation, optionally followed by the colour frame's copy into host memory (pinned or not).
+ * ms[3] receives the three kernel times.  Same results as the three calls above. */
+int hdt_resolve_frame(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size,
+                      int colors_kind, const void* colors_pod, size_t colors_pod_size,
+                      const double cam[3], const double ray_min[3], const double ray_ddx[3], const double ray_ddy[3],
+                      float shadow_bias, float fog_density, int with_shadows, uint32_t* host_colors_or_null, float ms[3]);
+
+/* Pipelined use (SURVEY.md §8b "optional hdt_*_async + hdt_sync pair"): enqueue a frame on the
+ * tracer's stream without waiting; hdt_sync() blocks until everything enqueued has finished and
+ * reports the first error.  hdt_timer_begin/end bracket any number of enqueued frames with CUDA
+ * events on that stream (device time, in milliseconds). */
+int hdt_resolve_frame_async(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size,
+                            int colors_kind, const void* colors_pod, size_t colors_pod_size,
+                            const double cam[3], const double ray_min[3], const double ray_ddx[3], const double ray_ddy[3],
+                            float shadow_bias, float fog_density, int with_shadows, uint32_t* host_colors_or_null);
+int hdt_sync(hdt_ctx* ctx);
+int hdt_timer_begin(hdt_ctx* ctx);
+int hdt_timer_end(hdt_ctx* ctx, float* ms);
+
+/* Number of pixels of the last paths frame with a non-null path (= shadow rays cast). */
+int hdt_count_hits(hdt_ctx* ctx, uint64_t* n_hits);
+
+/* DAGTracer::get_path (dag_tracer.cu:240-256): voxel under pixel (x, y) of the last paths frame. */
+int hdt_get_path(hdt_ctx* ctx, uint32_t x, uint32_t y, uint32_t out_xyz[3]);
+
+/* Full-frame read-back (the reference has none; its harness reads the cudaArrays): row-major,
+ * reference orientation (paths row r = camera row height-1-r, tracer.cu:251). */
+int hdt_read_paths(hdt_ctx* ctx, uint32_t* host_w_h_4);
+int hdt_read_colors(hdt_ctx* ctx, uint32_t* host_w_h);
+
+/* ---- multi-GPU plumbing (the collectives themselves are issued by the host layer) ----------- */
+/* This rank's compact tile buffers (owned tiles back to back, each tile row-major). */
+int hdt_partition_buffers(hdt_ctx* ctx, void** paths_dev, void** colors_dev, uint64_t* n_owned_tiles, uint64_t* max_tiles_per_rank);
+/* Rank 0: scatter `world` gathered compact colour buffers (each max_tiles_per_rank tiles) into the row-major frame. */
+int hdt_assemble_colors(hdt_ctx* ctx, const uint32_t* gathered_dev, uint32_t* frame_dev_or_null);
+/* Apply edit-dirtied spans to a replica: dst[range.dst_word + i] = payload[range.src_word + i]. */
+int hdt_apply_ranges(hdt_ctx* ctx, uint32_t* dst_dev, const uint32_t* payload_dev, const hdt_range* ranges_dev, uint32_t n_ranges);
+
+/* Kernel launches issued by this context since creation (bench bookkeeping). */
+uint64_t hdt_launch_count(const hdt_ctx* ctx);
+int hdt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HASHDAG_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes front-end of oracle/_ref/libhashdag_ref_d*_*.so -- the UNMODIFIED reference tracer
+(/root/reference/src/{tracer,dag_tracer}.cu + its HashDAG factory) compiled for sm_100a by
+oracle/build_ref.py.  TEST INFRASTRUCTURE: needs a GPU; used by the `-m gpu` parity tests, by
+tests/golden/make_golden.py and by `bench.py --impl reference-cuda`.
+
+The reference keeps its scene in globals, so one process can hold one scene per library variant.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path(depth, width, height):
+    return os.path.join(_HERE, "_ref", f"libhashdag_ref_d{depth}_{width}x{height}.so")
+
+
+def available(depth, width, height):
+    return os.path.exists(lib_path(depth, width, height))
+
+
+def _d(v):
+    v = np.asarray(v, dtype=np.float64).reshape(-1)
+    return (C.c_double * v.size)(*v.tolist())
+
+
+class RefTracer:
+    def __init__(self, depth, width, height, device=0):
+        path = lib_path(depth, width, height)
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `python oracle/build_ref.py` where /root/reference exists")
+        self.lib = l = C.CDLL(path)
+        assert (l.ref_levels(), l.ref_width(), l.ref_height()) == (depth, width, height)
+        self.depth, self.width, self.height = depth, width, height
+        d = C.POINTER(C.c_double)
+        l.ref_set_basic_dag.argtypes = [C.c_void_p, C.c_uint64]
+        l.ref_set_compressed_colors.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        l.ref_set_uncompressed_colors.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        l.ref_build_hash_dag.argtypes = [C.c_uint32, C.c_int]
+        l.ref_hash_info.argtypes = [C.POINTER(C.c_uint32)] * 3
+        l.ref_hash_copy.argtypes = [C.c_void_p, C.c_void_p]
+        l.ref_hash_colors_info.argtypes = [C.POINTER(C.c_uint64)] * 2
+        l.ref_hash_colors_copy.argtypes = [C.c_void_p, C.c_void_p]
+        l.ref_resolve_paths.restype = C.c_float
+        l.ref_resolve_paths.argtypes = [C.c_int, d, d, d, d]
+        l.ref_resolve_colors.restype = C.c_float
+        l.ref_resolve_colors.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32]
+        l.ref_resolve_shadows.restype = C.c_float
+        l.ref_resolve_shadows.argtypes = [C.c_int, d, d, d, d, C.c_float, C.c_float]
+        l.ref_read_paths.argtypes = [C.c_void_p]
+        l.ref_read_colors.argtypes = [C.c_void_p]
+        l.ref_write_colors.argtypes = [C.c_void_p]
+        if l.ref_init(device) != 0:
+            raise RuntimeError("ref_init failed (no CUDA device?)")
+        self.scene = None
+
+    def load_scene(self, scene, with_hash=True, with_colors=True, with_uncompressed=False):
+        assert scene.levels == self.depth
+        l = self.lib
+        self.scene = scene
+        l.ref_set_basic_dag(scene.basic.ctypes.data, scene.basic.size)
+        if with_colors:
+            l.ref_set_compressed_colors(scene.top_levels, scene.enclosed_leaves.ctypes.data, scene.enclosed_leaves.size,
+                                        scene.weights.ctypes.data, scene.weights.size, scene.blocks.ctypes.data, scene.blocks.size,
+                                        scene.macro_blocks.ctypes.data, scene.macro_blocks.size)
+        if with_uncompressed:
+            l.ref_set_uncompressed_colors(scene.top_levels, scene.enclosed_leaves.ctypes.data, scene.enclosed_leaves.size,
+                                          scene.uncompressed.ctypes.data, scene.uncompressed.size)
+        if with_hash:
+            hash_colors = with_colors and scene.levels - 2 > 10
+            l.ref_build_hash_dag(scene.hash_pool_top + 4096, int(hash_colors))
+
+    def hash_dag(self):
+        """(pool, page_table, first_node_index, pool_top) as built by the reference's own factory."""
+        f, t, s = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        assert self.lib.ref_hash_info(C.byref(f), C.byref(t), C.byref(s)) == 0
+        pool = np.empty(t.value * 512, dtype=np.uint32)
+        pt = np.empty(s.value, dtype=np.uint32)
+        self.lib.ref_hash_copy(pool.ctypes.data, pt.ctypes.data)
+        return pool, pt, f.value, t.value
+
+    def hash_colors(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        assert self.lib.ref_hash_colors_info(C.byref(a), C.byref(b)) == 0
+        nodes = np.empty(a.value, dtype=np.uint32)
+        offs = np.empty(b.value, dtype=np.uint64)
+        self.lib.ref_hash_colors_copy(nodes.ctypes.data, offs.ctypes.data)
+        return nodes, offs
+
+    def resolve_paths(self, dag_kind, camera, info):
+        return self.lib.ref_resolve_paths(dag_kind, _d(camera.position), _d(camera.rotation), _d(info.bounds_min), _d(info.bounds_max))
+
+    def resolve_colors(self, dag_kind, colors_kind, debug_colors=0, debug_level=0):
+        return self.lib.ref_resolve_colors(dag_kind, colors_kind, debug_colors, debug_level)
+
+    def resolve_shadows(self, dag_kind, camera, info, shadow_bias=1.0, fog_density=0.0):
+        return self.lib.ref_resolve_shadows(dag_kind, _d(camera.position), _d(camera.rotation), _d(info.bounds_min), _d(info.bounds_max),
+                                            shadow_bias, fog_density)
+
+    def read_paths(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint32)
+        assert self.lib.ref_read_paths(out.ctypes.data) == 0
+        return out
+
+    def read_colors(self):
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        assert self.lib.ref_read_colors(out.ctypes.data) == 0
+        return out
+
+    def write_colors(self, img):
+        img = np.ascontiguousarray(img, dtype=np.uint32)
+        assert self.lib.ref_write_colors(img.ctypes.data) == 0

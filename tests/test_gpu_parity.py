@@ -1,0 +1,213 @@
+"""GPU parity: the CUDA product, called through the C ABI, against the CPU oracle, against the
+committed golden frames and against the reference's own kernels (oracle/_ref) on the same inputs.
+Bit-exact for paths and colours; shaded colours bit-exact without fog, <= 1/255 with fog (exp/pow)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, get_scene, scene_cameras
+from hashdag_b200 import camera
+from oracle import hdo
+
+pytestmark = pytest.mark.gpu
+
+W, H = 320, 200
+
+
+@pytest.fixture(scope="module")
+def tr():
+    from hashdag_b200 import tracer
+    cache = {}
+
+    def get(levels, w=W, h=H):
+        if (levels, w, h) not in cache:
+            cache[(levels, w, h)] = tracer.DAGTracer(True, w, h, levels)
+        return cache[(levels, w, h)]
+    yield get
+    for t in cache.values():
+        t.close()
+
+
+def _info(s):
+    return camera.DAGInfo(s.bounds_min, s.bounds_max)
+
+
+def _diff(a, b):
+    a8 = a.view(np.uint8).astype(np.int16)
+    b8 = b.view(np.uint8).astype(np.int16)
+    return int(np.abs(a8 - b8).max())
+
+
+@pytest.mark.parametrize("levels,fp", [(12, 10), (13, 10), (16, 11), (17, 10)])
+@pytest.mark.parametrize("kind", ["basic", "hash"])
+def test_paths_colors_shadows_match_oracle(tr, levels, fp, kind):
+    from hashdag_b200 import tracer
+    s = get_scene(levels, fp)
+    t = tr(levels)
+    hashed = kind == "hash"
+    dag = (tracer.HashDAG if hashed else tracer.BasicDAG).from_scene(s)
+    odag = hdo.make_dag(s, hdo.DAG_HASH if hashed else hdo.DAG_BASIC)
+    with_hash_colors = hashed and s.has_hash_colors
+    if hashed and not with_hash_colors:
+        col = ocol = None
+    else:
+        col = (tracer.HashDAGColors if hashed else tracer.BasicDAGCompressedColors).from_scene(s)
+        ocol = hdo.make_colors(s, hdo.COLORS_HASH if hashed else hdo.COLORS_COMPRESSED)
+    total_hits = 0
+    for cam in scene_cameras(s, 3, fp):
+        prm = camera.trace_params(cam, _info(s), levels, W, H)
+        ms = t.resolve_paths(cam, _info(s), dag)
+        assert ms > 0
+        p = t.read_paths()
+        op, st = hdo.trace_paths(odag, W, H, prm)
+        assert np.array_equal(p, op), f"{(p != op).any(-1).sum()} path pixels differ"
+        total_hits += st["n_hit"]
+        if col is None:
+            continue
+        t.resolve_colors(dag, col)
+        c = t.read_colors()
+        oc, _ = hdo.trace_colors(odag, ocol, op)
+        assert np.array_equal(c, oc), f"{(c != oc).sum()} colour pixels differ"
+        t.resolve_shadows(cam, _info(s), dag, 1.0, 0.0)
+        sh = t.read_colors()
+        osh, _ = hdo.trace_shadows(odag, prm, op, oc, 1.0, 0.0)
+        assert np.array_equal(sh, osh), f"{(sh != osh).sum()} shaded pixels differ"
+        t.resolve_colors(dag, col)
+        t.resolve_shadows(cam, _info(s), dag, 2.5, 5.0)
+        fg = t.read_colors()
+        ofg, _ = hdo.trace_shadows(odag, prm, op, oc, 2.5, 5.0)
+        assert _diff(fg, ofg) <= 1
+        assert (fg != ofg).mean() < 1e-3
+    assert total_hits > 0
+
+
+@pytest.mark.parametrize("dbg", range(1, 8))
+def test_debug_color_modes_match_oracle(tr, dbg):
+    from hashdag_b200 import tracer
+    s = get_scene(13, 10)
+    t = tr(13)
+    cam = scene_cameras(s, 1, 10)[0]
+    prm = camera.trace_params(cam, _info(s), 13, W, H)
+    for hashed in (False, True):
+        dag = (tracer.HashDAG if hashed else tracer.BasicDAG).from_scene(s)
+        col = (tracer.HashDAGColors if hashed else tracer.BasicDAGCompressedColors).from_scene(s)
+        odag = hdo.make_dag(s, hdo.DAG_HASH if hashed else hdo.DAG_BASIC)
+        ocol = hdo.make_colors(s, hdo.COLORS_HASH if hashed else hdo.COLORS_COMPRESSED)
+        t.resolve_paths(cam, _info(s), dag)
+        p = t.read_paths()
+        for lvl in (0, 4, 11):
+            t.resolve_colors(dag, col, dbg, lvl)
+            oc, _ = hdo.trace_colors(odag, ocol, p, dbg, lvl)
+            assert np.array_equal(t.read_colors(), oc), f"debug mode {dbg} level {lvl} hashed={hashed}"
+
+
+def test_uncompressed_and_error_colors_match_oracle(tr):
+    from hashdag_b200 import tracer
+    s = get_scene(12, 10, uncompressed=True)
+    t = tr(12)
+    cam = scene_cameras(s, 1, 10)[0]
+    dag = tracer.BasicDAG.from_scene(s)
+    odag = hdo.make_dag(s, hdo.DAG_BASIC)
+    t.resolve_paths(cam, _info(s), dag)
+    p = t.read_paths()
+    unc = tracer.BasicDAGUncompressedColors.from_scene(s)
+    comp = tracer.BasicDAGCompressedColors.from_scene(s)
+    t.resolve_colors(dag, unc)
+    assert np.array_equal(t.read_colors(), hdo.trace_colors(odag, hdo.make_colors(s, hdo.COLORS_UNCOMPRESSED), p)[0])
+    t.resolve_colors(dag, tracer.BasicDAGColorErrors(comp, unc))
+    assert np.array_equal(t.read_colors(), hdo.trace_colors(odag, hdo.make_colors(s, hdo.COLORS_ERRORS), p)[0])
+
+
+def test_get_path_and_frame_call(tr):
+    from hashdag_b200 import tracer
+    s = get_scene(13, 10)
+    t = tr(13)
+    cam = scene_cameras(s, 1, 10)[0]
+    dag, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
+    t.resolve_paths(cam, _info(s), dag)
+    p = t.read_paths()
+    for (x, y) in ((0, 0), (W // 2, H // 2), (W - 1, H - 1), (17, 133)):
+        assert t.get_path(x, y) == tuple(int(v) for v in p[y, x, :3])
+    t.resolve_colors(dag, col)
+    t.resolve_shadows(cam, _info(s), dag, 1.0, 0.0)
+    want = t.read_colors()
+    host = np.zeros((H, W), dtype=np.uint32)
+    ms = t.resolve_frame(cam, _info(s), dag, col, 1.0, 0.0, True, host)
+    assert all(m > 0 for m in ms)
+    assert np.array_equal(host, want) and np.array_equal(t.read_paths(), p)
+
+
+def test_abi_rejects_bad_arguments(tr):
+    from hashdag_b200 import tracer
+    s = get_scene(12, 10)
+    t = tr(12)
+    dag = tracer.BasicDAG.from_scene(s)
+    cam = scene_cameras(s, 1, 10)[0]
+
+    class Short:
+        kind = tracer.DAG_BASIC
+
+        def pod(self):
+            return dag.pod()[:8]
+    with pytest.raises(tracer.TracerError):
+        t.resolve_paths(cam, _info(s), Short())
+    with pytest.raises(tracer.TracerError):
+        t.get_path(W, 0)
+    with pytest.raises(tracer.TracerError):   # HashDAG colours with a BasicDAG: not an instantiation the tracer has
+        t.resolve_colors(dag, tracer.HashDAGColors(dag.data, dag.data, tracer.CompressedColorLeaf(None, None, None)))
+    with pytest.raises(tracer.TracerError):
+        tracer.DAGTracer(True, 64, 64, 40)
+
+
+def test_partitioned_render_assembles_to_the_whole_frame(tr):
+    """Screen-tile partition (rank r of n renders tiles t % n == r): gathered == unpartitioned frame."""
+    import torch
+    from hashdag_b200 import tracer
+    s = get_scene(13, 10)
+    cam = scene_cameras(s, 1, 10)[0]
+    dag, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
+    whole = tr(13)
+    whole.resolve_frame(cam, _info(s), dag, col, 1.0, 0.0, True)
+    want_c, want_p = whole.read_colors(), whole.read_paths()
+    world, tl = 3, 5
+    parts = []
+    acc_c = np.zeros_like(want_c)
+    acc_p = np.zeros_like(want_p)
+    for r in range(world):
+        t = tracer.DAGTracer(True, W, H, 13)
+        t.set_partition(r, world, tl)
+        t.resolve_frame(cam, _info(s), dag, col, 1.0, 0.0, True)
+        acc_c |= t.read_colors()
+        acc_p |= t.read_paths()
+        _, cptr, n_owned, max_tiles = t.partition_buffers()
+        n = max_tiles << (2 * tl)
+        buf = torch.empty(n, dtype=torch.int32, device="cuda")
+        import ctypes
+        torch.cuda.synchronize()
+        assert ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(cptr), ctypes.c_size_t(n * 4), 3) == 0
+        parts.append(buf)
+        t.close()
+    assert np.array_equal(acc_c, want_c) and np.array_equal(acc_p, want_p)
+    gathered = torch.cat(parts)
+    t0 = tracer.DAGTracer(True, W, H, 13)
+    t0.set_partition(0, world, tl)
+    frame = torch.zeros(H * W, dtype=torch.int32, device="cuda")
+    t0.assemble_colors(gathered, frame)
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32).reshape(H, W), want_c)
+    # host mirror of the same layout
+    from hashdag_b200 import partition
+    packed = [partition.pack_compact(want_c, r, world, tl) for r in range(world)]
+    assert np.array_equal(partition.assemble(packed, W, H, tl), want_c)
+    assert np.array_equal(packed[1].reshape(-1), parts[1].cpu().numpy().view(np.uint32))
+    t0.close()
+
+
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cuda_against_reference_golden_frames(path):
+    from golden_util import check_golden
+    check_golden(path, impl="cuda")

@@ -1,0 +1,76 @@
+"""GPU: the UNMODIFIED reference kernels (oracle/_ref, built by oracle/build_ref.py) against the
+oracle and the product on identical inputs.  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from hashdag_b200 import camera
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(gu.RECIPES))
+def test_reference_vs_oracle_vs_product(name):
+    from hashdag_b200 import tracer
+    scene = gu.recipe_scene(name)
+    if not ref.available(scene.levels, gu.W, gu.H):
+        pytest.skip("oracle/_ref variant not built")
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    rt = ref.RefTracer(scene.levels, gu.W, gu.H)
+    rt.load_scene(scene)
+    # the reference's own BasicDAG -> HashDAG conversion reproduces our packer bit for bit
+    pool, pt, first, top = rt.hash_dag()
+    assert first == scene.hash_first_node_index and top == scene.hash_pool_top
+    assert np.array_equal(pt, scene.hash_page_table)
+    assert np.array_equal(pool, scene.hash_pool)
+    if scene.has_hash_colors:
+        nodes, offs = rt.hash_colors()
+        assert np.array_equal(nodes, scene.color_nodes) and np.array_equal(offs, scene.color_offsets)
+    t = tracer.DAGTracer(True, gu.W, gu.H, scene.levels)
+    objs = {"basic": (t, tracer.BasicDAG.from_scene(scene), tracer.BasicDAGCompressedColors.from_scene(scene))}
+    if scene.has_hash_colors:
+        objs["hash"] = (t, tracer.HashDAG.from_scene(scene), tracer.HashDAGColors.from_scene(scene))
+    for i, pose in enumerate(gu.recipe_poses(scene)):
+        for kind, (dk, ck) in (("basic", (0, 1)), ("hash", (1, 3))):
+            if kind not in objs:
+                continue
+            rt.resolve_paths(dk, pose, info)
+            rp = rt.read_paths()
+            rt.resolve_colors(dk, ck)
+            rc = rt.read_colors()
+            rt.resolve_shadows(dk, pose, info, 1.0, 0.0)
+            rs = rt.read_colors()
+            rt.resolve_colors(dk, ck)
+            rt.resolve_shadows(dk, pose, info, 1.0, gu.FOG)
+            rf = rt.read_colors()
+            for impl in ("oracle", "cuda"):
+                p, c, s, f = gu.render(impl, scene, kind, pose, gu.FOG, objs[kind])
+                tag = f"{name} pose {i} {kind} {impl}"
+                assert np.array_equal(p, rp), f"{tag}: {(p != rp).any(-1).sum()} path pixels differ from the reference"
+                assert np.array_equal(c, rc), f"{tag}: {(c != rc).sum()} colour pixels differ"
+                assert np.array_equal(s, rs), f"{tag}: {(s != rs).sum()} shaded pixels differ"
+                assert gu.channel_diff(f, rf) <= 1, f"{tag}: fog differs by more than 1/255"
+    t.close()
+
+
+def test_reference_debug_modes_vs_product():
+    from hashdag_b200 import tracer
+    scene = gu.recipe_scene("d13")
+    if not ref.available(13, gu.W, gu.H):
+        pytest.skip("oracle/_ref variant not built")
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    rt = ref.RefTracer(13, gu.W, gu.H)
+    rt.load_scene(scene)
+    t = tracer.DAGTracer(True, gu.W, gu.H, 13)
+    pose = gu.recipe_poses(scene)[0]
+    for dk, ck, dag, col in ((0, 1, tracer.BasicDAG.from_scene(scene), tracer.BasicDAGCompressedColors.from_scene(scene)),
+                             (1, 3, tracer.HashDAG.from_scene(scene), tracer.HashDAGColors.from_scene(scene))):
+        rt.resolve_paths(dk, pose, info)
+        t.resolve_paths(pose, info, dag)
+        for dbg in range(1, 8):
+            for lvl in (0, 5, 11):
+                rt.resolve_colors(dk, ck, dbg, lvl)
+                t.resolve_colors(dag, col, dbg, lvl)
+                assert np.array_equal(t.read_colors(), rt.read_colors()), f"debug {dbg} level {lvl} dag {dk}"
+    t.close()
