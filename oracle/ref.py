@@ -7,6 +7,7 @@ The reference keeps its scene in globals, so one process can hold one scene per 
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 
@@ -57,6 +58,13 @@ class RefTracer:
         if l.ref_init(device) != 0:
             raise RuntimeError("ref_init failed (no CUDA device?)")
         self.scene = None
+        atexit.register(self.close)
+
+    def close(self):
+        """Release the reference's allocations (its leak check aborts the process otherwise)."""
+        if self.lib is not None:
+            self.lib.ref_shutdown()
+            self.lib = None
 
     def load_scene(self, scene, with_hash=True, with_colors=True, with_uncompressed=False):
         assert scene.levels == self.depth
@@ -114,3 +122,21 @@ class RefTracer:
     def write_colors(self, img):
         img = np.ascontiguousarray(img, dtype=np.uint32)
         assert self.lib.ref_write_colors(img.ctypes.data) == 0
+
+
+_SHARED = {}
+
+
+def shared(scene, width, height, key, **load_kwargs):
+    """One RefTracer per library variant and process (the reference keeps its scene in globals and
+    cannot load a second one); `key` names the scene so a different one is refused, not mixed up."""
+    k = (scene.levels, width, height)
+    if k in _SHARED:
+        rt, have = _SHARED[k]
+        if have != key:
+            raise RuntimeError(f"reference variant d{k[0]}_{k[1]}x{k[2]} already holds scene {have!r}")
+        return rt
+    rt = RefTracer(scene.levels, width, height)
+    rt.load_scene(scene, **load_kwargs)
+    _SHARED[k] = (rt, key)
+    return rt

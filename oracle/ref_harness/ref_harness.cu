@@ -75,6 +75,22 @@ int ref_init(int device)
     return 0;
 }
 
+// Free everything the reference allocated, the way main.cpp does before returning, so that its
+// leak check (Memory::~Memory, memory.cpp:145-157: abort() on leaks) stays quiet at process exit.
+int ref_shutdown()
+{
+    if (!g_tracer) return 0;
+    cudaDeviceSynchronize();
+    if (g_hasHashColors) { g_hashColors.free(); g_hasHashColors = false; }
+    if (g_hasHash) { g_hash.free(); g_hasHash = false; }
+    if (g_compressed.is_valid()) g_compressed.free();
+    else if (g_compressed.enclosedLeaves.is_valid()) g_compressed.enclosedLeaves.free();
+    if (g_uncompressed.is_valid()) g_uncompressed.free();
+    if (g_basic.is_valid()) g_basic.free();
+    g_tracer.reset();
+    return 0;
+}
+
 int ref_set_basic_dag(const uint32_t* words, uint64_t n)
 {
     // like BasicDAGFactory::load_dag_from_file: managed memory (basic_dag.cpp:104-117)
@@ -118,6 +134,12 @@ int ref_build_hash_dag(uint32_t poolPages, int withColors)
     g_hasHash = true;
     if (withColors) {
         HashDAGFactory::load_colors_from_DAG(g_hashColors, g_basic, g_compressed);
+        // Under BENCHMARK the factory "reserves" nodes_GPU/leaves_GPU right after the first upload
+        // (hash_dag_colors.h:244-250); that goes through Memory::realloc_impl, whose GPU branch calls
+        // cuda_memcpy_impl(..., cudaMemcpyDefault) -- a kind that function silently ignores
+        // (memory.cpp:159-188, :268-273) -- so the device copy of the colour tree is lost.  The engine
+        // repairs it with the upload it issues after every edit (hash_dag.h:398); do the same here.
+        g_hashColors.upload_to_gpu(false);
         g_hasHashColors = true;
     }
     return 0;

@@ -24,9 +24,8 @@ def main(out_dir):
     for name in gu.RECIPES:
         scene = gu.recipe_scene(name)
         info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
-        rt = ref.RefTracer(scene.levels, gu.W, gu.H)
+        rt = ref.shared(scene, gu.W, gu.H, name)
         has_hash_colors = scene.levels - 2 > 10
-        rt.load_scene(scene, with_hash=True, with_colors=True)
         poses = gu.recipe_poses(scene)
         arrays = {}
         for i, pose in enumerate(poses):

@@ -17,8 +17,7 @@ def test_reference_vs_oracle_vs_product(name):
     if not ref.available(scene.levels, gu.W, gu.H):
         pytest.skip("oracle/_ref variant not built")
     info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
-    rt = ref.RefTracer(scene.levels, gu.W, gu.H)
-    rt.load_scene(scene)
+    rt = ref.shared(scene, gu.W, gu.H, name)
     # the reference's own BasicDAG -> HashDAG conversion reproduces our packer bit for bit
     pool, pt, first, top = rt.hash_dag()
     assert first == scene.hash_first_node_index and top == scene.hash_pool_top
@@ -60,8 +59,7 @@ def test_reference_debug_modes_vs_product():
     if not ref.available(13, gu.W, gu.H):
         pytest.skip("oracle/_ref variant not built")
     info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
-    rt = ref.RefTracer(13, gu.W, gu.H)
-    rt.load_scene(scene)
+    rt = ref.shared(scene, gu.W, gu.H, "d13")
     t = tracer.DAGTracer(True, gu.W, gu.H, 13)
     pose = gu.recipe_poses(scene)[0]
     for dk, ck, dag, col in ((0, 1, tracer.BasicDAG.from_scene(scene), tracer.BasicDAGCompressedColors.from_scene(scene)),
