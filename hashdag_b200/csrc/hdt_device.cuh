@@ -6,6 +6,7 @@
 // compiled with -fmad=false so the compiler adds none of its own.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 
 namespace hdt {
@@ -79,10 +80,235 @@ __device__ __forceinline__ u32 second_child_mask(uint2 leaf, u32 firstChild)
 
 struct Ray { float ox, oy, oz, dx, dy, dz, ix, iy, iz; };
 
+// Comparison -> all-ones / zero word (one FSET instead of FSETP + SEL).  Ordered compares: false
+// on NaN, like the C++ comparisons of the reference.
+__device__ __forceinline__ u32 set_ge(float a, float b) { u32 d; asm("set.ge.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ u32 set_le(float a, float b) { u32 d; asm("set.le.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); return d; }
+
+// A ray is "tame" when no NaN can reach the slab min/max below: finite origin and |1/d| <= 2^100
+// on every axis (so radius*|1/d| is finite and centre*1/d cannot be 0*inf or inf-inf).  Only then
+// may the reference's ternary max/min (cuda_math.h:42-44) be replaced by fmaxf/fminf, which differ
+// from it solely when the second operand is NaN.  Axis-parallel rays take the exact-ternary path.
+__device__ __forceinline__ bool ray_is_tame(const Ray& r)
+{
+    const float lim = 1.2676506e30f;  // 2^100
+    return fabsf(r.ix) <= lim && fabsf(r.iy) <= lim && fabsf(r.iz) <= lim && fabsf(r.ox) <= 3.0e38f && fabsf(r.oy) <= 3.0e38f && fabsf(r.oz) <= 3.0e38f;
+}
+
+// One of the three axis-plane tests of tracer.cu:91-133: if the ray meets the node's mid-plane at
+// t within [tmin, tmax], OR in the octants on the side(s) of the crossing point q = (q1, q2), each
+// side decided with an epsilon band (lo = centre - eps, hi = centre + eps).  Written in PTX so that
+// it becomes exactly 6 FSETP (the range predicate rides on the .AND input of the first pair, so an
+// out-of-range plane yields A = 0), 4 SEL, 2 adds and one LOP3 -- no branches, no extra selects.
+template <u32 HI1, u32 LO1, u32 HI2, u32 LO2>
+__device__ __forceinline__ u32 plane_mask(float tmin, float tmax, float t, float q1, float lo1, float hi1, float q2, float lo2, float hi2)
+{
+    u32 out;
+    asm("{\n\t"
+        ".reg .pred pin, pa, pb, pc, pd;\n\t"
+        ".reg .u32 a, b, c, d;\n\t"
+        "setp.le.f32 pin, %1, %3;\n\t"
+        "setp.le.and.f32 pin, %3, %2, pin;\n\t"
+        "setp.ge.and.f32 pa, %4, %5, pin;\n\t"
+        "setp.le.and.f32 pb, %4, %6, pin;\n\t"
+        "setp.ge.f32 pc, %7, %8;\n\t"
+        "setp.le.f32 pd, %7, %9;\n\t"
+        "selp.u32 a, %10, 0, pa;\n\t"
+        "selp.u32 b, %11, 0, pb;\n\t"
+        "selp.u32 c, %12, 0, pc;\n\t"
+        "selp.u32 d, %13, 0, pd;\n\t"
+        "add.u32 a, a, b;\n\t"
+        "add.u32 c, c, d;\n\t"
+        "and.b32 %0, a, c;\n\t"
+        "}"
+        : "=r"(out)
+        : "f"(tmin), "f"(tmax), "f"(t), "f"(q1), "f"(lo1), "f"(hi1), "f"(q2), "f"(lo2), "f"(hi2), "n"(HI1), "n"(LO1), "n"(HI2), "n"(LO2));
+    return out;
+}
+
+// tracer.cu:19-136 for the node with centre (cx,cy,cz) and half-size `radius`.
+//  * Centre and radius are exact floats (multiples of 0.5 below 2^24, radius a power of two), so
+//    radius*|inv| is exact and tmid -+ radius*|inv| equals fma(-+radius, |inv|, tmid) bit for bit.
+//  * The three plane tests are evaluated without branches: every comparison becomes a 0/~0 word and
+//    the reference's byte constants are merged with LOP3.  Bits above bit 7 of the result are junk;
+//    the caller ANDs with an 8-bit child mask.
+template <bool isRoot, bool TAME>
+__device__ __forceinline__ u32 intersection_mask(float cx, float cy, float cz, float radius, const Ray& r)
+{
+    const float rx = __fsub_rn(cx, r.ox), ry = __fsub_rn(cy, r.oy), rz = __fsub_rn(cz, r.oz);
+    const float tx = __fmul_rn(rx, r.ix), ty = __fmul_rn(ry, r.iy), tz = __fmul_rn(rz, r.iz);
+    const float nr = -radius;
+    const float ax = __fmaf_rn(nr, fabsf(r.ix), tx), ay = __fmaf_rn(nr, fabsf(r.iy), ty), az = __fmaf_rn(nr, fabsf(r.iz), tz);
+    const float bx = __fmaf_rn(radius, fabsf(r.ix), tx), by = __fmaf_rn(radius, fabsf(r.iy), ty), bz = __fmaf_rn(radius, fabsf(r.iz), tz);
+    float tmin, tmax;
+    if (TAME) {
+        tmin = fmaxf(fmaxf(ax, ay), fmaxf(az, 0.0f));
+        tmax = fminf(fminf(bx, by), bz);
+    } else {
+        const float ayz = (ay > az) ? ay : az;
+        const float a3 = (ax > ayz) ? ax : ayz;
+        tmin = fmaxf(a3, 0.0f);
+        const float byz = (by < bz) ? by : bz;
+        tmax = (bx < byz) ? bx : byz;
+    }
+    if (isRoot && (tmin >= tmax)) return 0;
+
+    const float h = __fmul_rn(0.5f, __fadd_rn(tmin, tmax));
+    u32 mask = 1u << (((__fmul_rn(h, r.dx) >= rx) ? 4u : 0u) + ((__fmul_rn(h, r.dy) >= ry) ? 2u : 0u) + ((__fmul_rn(h, r.dz) >= rz) ? 1u : 0u));
+
+    // Plane tests without branches (see plane_mask): an out-of-range plane contributes nothing.
+    const float eps = 1e-4f;
+    const float rxm = __fsub_rn(rx, eps), rxp = __fadd_rn(rx, eps);
+    const float rym = __fsub_rn(ry, eps), ryp = __fadd_rn(ry, eps);
+    const float rzm = __fsub_rn(rz, eps), rzp = __fadd_rn(rz, eps);
+    mask |= plane_mask<0xCC, 0x33, 0xAA, 0x55>(tmin, tmax, tx, __fmul_rn(tx, r.dy), rym, ryp, __fmul_rn(tx, r.dz), rzm, rzp);
+    mask |= plane_mask<0xF0, 0x0F, 0xAA, 0x55>(tmin, tmax, ty, __fmul_rn(ty, r.dx), rxm, rxp, __fmul_rn(ty, r.dz), rzm, rzp);
+    mask |= plane_mask<0xF0, 0x0F, 0xCC, 0x33>(tmin, tmax, tz, __fmul_rn(tz, r.dx), rxm, rxp, __fmul_rn(tz, r.dy), rym, ryp);
+    return mask;
+}
+
+// Shared-memory tables, filled once per CTA:
+//   child[order*256 + mask] = next_child(order, mask) (tracer.cu:7-17): first set bit of mask in the
+//                             order child ^ order, child = 0..7;
+//   step[c]                 = (+-1, +-1, +-1, 1<<c): direction of child c's centre from its parent's
+//                             (child bit 4 -> x, 2 -> y, 1 -> z, path.h:20-28) and its mask bit.
+struct TraverseTables {
+    float4 step[8];
+    u8 child[8 * 256];
+};
+
+static_assert(sizeof(TraverseTables) % 16 == 0, "copied as uint4");
+
+// Host-side initialisation (once per context); CTAs copy the 2176 bytes with 16-byte loads.
+inline void build_tables(TraverseTables& t)
+{
+    for (u32 i = 0; i < 8 * 256; ++i) {
+        const u32 order = i >> 8, mask = i & 255;
+        u32 res = 0;
+        for (int child = 7; child >= 0; --child) {
+            const u32 c = u32(child) ^ order;
+            if (mask & (1u << c)) res = c;
+        }
+        t.child[i] = u8(res);
+    }
+    for (u32 c = 0; c < 8; ++c) {
+        const u32 bit = 1u << c;
+        float w;
+        memcpy(&w, &bit, 4);
+        t.step[c] = make_float4((c & 4) ? 1.f : -1.f, (c & 2) ? 1.f : -1.f, (c & 1) ? 1.f : -1.f, w);
+    }
+}
+
+__device__ __forceinline__ void load_tables(TraverseTables& dst, const TraverseTables* __restrict__ src)
+{
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(&dst);
+    for (u32 i = threadIdx.x; i < sizeof(TraverseTables) / 16; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+// Stack DFS shared by trace_paths (ORDERED: children in ray order, first voxel wins,
+// tracer.cu:166-249) and trace_shadows (!ORDERED: highest child first, any voxel,
+// tracer.cu:458-542).  Same nodes visited in the same order as the reference's loop; what differs
+// is bookkeeping, chosen because the loop is ALU-pipe bound on sm_100a (profiles/):
+//   * the node is tracked by its float centre and radius instead of the integer Path: descending
+//     adds +-radius/2 per axis (one table load + three FFMA), ascending re-aligns the centre with
+//     four exact FADDs per axis (round-to-multiple by the 1.5*2^23 trick); every value involved is
+//     a multiple of 0.5 below 2^24, so all of it is exact and equals float(path << shift) + radius;
+//   * `pending` has bit L set iff stack[L] still has unvisited children: ascending is one FLO
+//     instead of a chain of dependent local loads, and exhausted entries are never stored;
+//   * one intersection_mask call site after the (divergent) child fetch instead of three;
+//   * HashDAG handles are physical: one page-table lookup per node instead of one per word.
+// Per-ray DFS state.  Scalars only, so it stays in registers; the stack (one uint2 per level:
+// .x = handle, .y = childMask | visitMask << 8) is a separate local-memory array.
+using WalkStack = uint2[kMaxLevels];
+
+template <class DAG>
+struct Walker {
+    u32 level, pending, handle, cm, vm;
+    uint2 leaf;
+    float radius, cx, cy, cz;
+
+    template <bool TAME>
+    __device__ __forceinline__ void start(const DAG& dag, const u32 levels, const Ray& ray)
+    {
+        level = 0; pending = 0; leaf = make_uint2(0, 0);
+        radius = __uint_as_float((127u + levels - 1u) << 23);   // 2^(levels-1)
+        cx = cy = cz = radius;
+        handle = dag.root();
+        cm = dag.header(handle) & 0xFF;
+        vm = cm & intersection_mask<true, TAME>(cx, cy, cz, radius, ray);
+    }
+
+    // One descent (preceded by an ascent if the current node is exhausted).
+    // Returns 0: keep going, 1: reached a voxel (cx,cy,cz = its centre), 2: left the DAG.
+    template <bool ORDERED, bool TAME>
+    __device__ __forceinline__ int step(const DAG& dag, const u32 levels, const Ray& ray, const TraverseTables& tab, const u32 order, WalkStack& stack)
+    {
+        const u32 leafLevel = levels - 2;
+        if (vm == 0) {
+            if (pending == 0) return 2;
+            const u32 nl = 31 - __clz(pending);
+            pending ^= 1u << nl;
+            const uint2 e = stack[nl];
+            handle = e.x; cm = e.y & 0xFF; vm = e.y >> 8;
+            // centre of the ancestor `level - nl` levels up: it is the cell of size S = 2*ra that
+            // contains the current centre.  (c - ra) lies strictly inside (corner - S/2, corner + S/2),
+            // so rounding it to a multiple of S (add/subtract 1.5*2^23*S) yields the corner exactly.
+            const float ra = __uint_as_float(__float_as_uint(radius) + ((level - nl) << 23));
+            const float magic = __fmul_rn(ra, 25165824.0f);   // 1.5 * 2^24 * ra = 1.5 * 2^23 * S
+            cx = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(cx, ra), magic), magic), ra);
+            cy = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(cy, ra), magic), magic), ra);
+            cz = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(cz, ra), magic), magic), ra);
+            radius = ra;
+            level = nl;
+        }
+        const u32 child = ORDERED ? u32(tab.child[(order << 8) | vm]) : (31 - __clz(vm));
+        const float4 st = tab.step[child];
+        vm &= ~__float_as_uint(st.w);
+        if (vm) { stack[level] = make_uint2(handle, cm | (vm << 8)); pending |= 1u << level; }
+        radius = __fmul_rn(radius, 0.5f);
+        cx = __fmaf_rn(st.x, radius, cx); cy = __fmaf_rn(st.y, radius, cy); cz = __fmaf_rn(st.z, radius, cz);
+        ++level;
+        if (level == levels) return 1;
+        if (level <= leafLevel) {
+            const u32 next = dag.child(handle, __popc(cm & (__float_as_uint(st.w) - 1u)) + 1);
+            if (level < leafLevel) {
+                handle = next;
+                cm = dag.header(next) & 0xFF;
+            } else {
+                leaf = dag.leaf(next);
+                cm = first_child_mask(leaf);
+            }
+        } else {
+            cm = second_child_mask(leaf, child);
+        }
+        vm = cm & intersection_mask<false, TAME>(cx, cy, cz, radius, ray);
+        return 0;
+    }
+    // voxel coordinates once step() returned 1: centre = corner + 0.5
+    __device__ __forceinline__ void voxel(u32& x, u32& y, u32& z) const { x = __float2uint_rz(cx); y = __float2uint_rz(cy); z = __float2uint_rz(cz); }
+};
+
+template <class DAG, bool ORDERED, bool TAME>
+__device__ __forceinline__ bool traverse(const DAG& dag, const u32 levels, const Ray& ray, const TraverseTables& tab, const u32 order,
+                                         u32& outx, u32& outy, u32& outz)
+{
+    Walker<DAG> w;
+    WalkStack stack;
+    w.template start<TAME>(dag, levels, ray);
+    for (;;) {
+        const int r = w.template step<ORDERED, TAME>(dag, levels, ray, tab, order, stack);
+        if (r == 1) { w.voxel(outx, outy, outz); return true; }
+        if (r == 2) { outx = outy = outz = 0; return false; }
+    }
+}
+
+#ifdef HDT_TRAVERSE_V1
+// ---- first version (integer Path, branchy plane tests), kept for A/B measurements ----
 // tracer.cu:19-136.  Centre and radius are exact floats (integers / halves below 2^24, power-of-two
 // radius), so radius*|inv| is exact and pmin/pmax are the same whether or not they are fused.
 template <bool isRoot>
-__device__ __forceinline__ u32 intersection_mask(u32 level, u32 levels, u32 px, u32 py, u32 pz, const Ray& r)
+__device__ __forceinline__ u32 intersection_mask_v1(u32 level, u32 levels, u32 px, u32 py, u32 pz, const Ray& r)
 {
     const u32 shift = levels - level;
     const float radius = __uint2float_rn(1u << (shift - 1));
@@ -135,7 +361,7 @@ __device__ __forceinline__ u32 intersection_mask(u32 level, u32 levels, u32 px, 
 
 // next_child (tracer.cu:7-17) as a table: lut[order*256 + mask] = first set bit of mask in the
 // order child ^ order, child = 0..7.  2 KB of shared memory, filled once per CTA.
-__device__ __forceinline__ void fill_next_child_lut(u8* lut)
+__device__ __forceinline__ void fill_next_child_lut_v1(u8* lut)
 {
     for (u32 i = threadIdx.x; i < 8 * 256; i += blockDim.x) {
         const u32 order = i >> 8, mask = i & 255;
@@ -154,10 +380,10 @@ __device__ __forceinline__ void fill_next_child_lut(u8* lut)
 // visited or in which order:
 //   * `pending` has bit L set iff stack[L] still has unvisited children, so ascending is one
 //     clz instead of a chain of dependent local-memory loads, and empty entries are never stored;
-//   * one intersection_mask call site after the (divergent) child fetch instead of three;
+//   * one intersection_mask_v1 call site after the (divergent) child fetch instead of three;
 //   * HashDAG handles are physical, one page-table lookup per node instead of one per word.
 template <class DAG, bool ORDERED>
-__device__ __forceinline__ bool traverse(const DAG& dag, const u32 levels, const Ray& ray, const u8* __restrict__ lut, const u32 order,
+__device__ __forceinline__ bool traverse_v1(const DAG& dag, const u32 levels, const Ray& ray, const u8* __restrict__ lut, const u32 order,
                                          u32& outx, u32& outy, u32& outz)
 {
     const u32 leafLevel = levels - 2;
@@ -167,7 +393,7 @@ __device__ __forceinline__ bool traverse(const DAG& dag, const u32 levels, const
 
     u32 handle = dag.root();
     u32 cm = dag.header(handle) & 0xFF;
-    u32 vm = cm & intersection_mask<true>(0, levels, 0, 0, 0, ray);
+    u32 vm = cm & intersection_mask_v1<true>(0, levels, 0, 0, 0, ray);
 
     for (;;) {
         if (vm == 0) {
@@ -196,9 +422,11 @@ __device__ __forceinline__ bool traverse(const DAG& dag, const u32 levels, const
         } else {
             cm = second_child_mask(leaf, child);
         }
-        vm = cm & intersection_mask<false>(level, levels, px, py, pz, ray);
+        vm = cm & intersection_mask_v1<false>(level, levels, px, py, pz, ray);
     }
 }
+
+#endif
 
 struct CameraParams { double cam[3], rayMin[3], ddx[3], ddy[3]; };  // TracePathsParams, tracer.h:81-91
 

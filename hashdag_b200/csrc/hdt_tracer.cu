@@ -4,6 +4,7 @@
 #include "../../include/hashdag_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -44,10 +45,10 @@ __device__ __forceinline__ bool thread_pixel(const PixelMap& m, u32& x, u32& y)
 // ---------------------------------------------------------------------------------------------
 template <class DAG>
 __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const CameraParams cam, const DAG dag, const u32 levels, const PixelMap map,
-                                                                    uint4* __restrict__ paths)
+                                                                    uint4* __restrict__ paths, const TraverseTables* __restrict__ tables)
 {
-    __shared__ u8 lut[8 * 256];
-    fill_next_child_lut(lut);
+    __shared__ TraverseTables tab;
+    load_tables(tab, tables);
     __syncthreads();
     u32 x, y;
     if (!thread_pixel(map, x, y)) return;
@@ -61,7 +62,12 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const Camera
     const u32 order = (ray.dx < 0.f ? 4u : 0u) + (ray.dy < 0.f ? 2u : 0u) + (ray.dz < 0.f ? 1u : 0u);
 
     u32 px, py, pz;
-    traverse<DAG, true>(dag, levels, ray, lut, order, px, py, pz);
+#ifdef HDT_TRAVERSE_V1
+    traverse_v1<DAG, true>(dag, levels, ray, tab.child, order, px, py, pz);
+#else
+    if (ray_is_tame(ray)) traverse<DAG, true, true>(dag, levels, ray, tab, order, px, py, pz);
+    else traverse<DAG, true, false>(dag, levels, ray, tab, order, px, py, pz);
+#endif
     paths[map.index(x, y)] = make_uint4(px, py, pz, 0);
 }
 
@@ -86,8 +92,12 @@ struct ShadowParams { float shadowBias, fogDensity; float sunX, sunY, sunZ; };
 
 template <class DAG>
 __global__ void __launch_bounds__(kBlockThreads) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
-                                                                      const PixelMap map, const uint4* __restrict__ paths, u32* __restrict__ colors)
+                                                                      const PixelMap map, const uint4* __restrict__ paths, u32* __restrict__ colors,
+                                                                      const TraverseTables* __restrict__ tables)
 {
+    __shared__ TraverseTables tab;
+    load_tables(tab, tables);
+    __syncthreads();
     u32 x, y;
     if (!thread_pixel(map, x, y)) return;
     const u64 idx = map.index(x, y);
@@ -129,7 +139,12 @@ __global__ void __launch_bounds__(kBlockThreads) trace_shadows_kernel(const Came
     ray.dx = sp.sunX; ray.dy = sp.sunY; ray.dz = sp.sunZ;
     ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
     u32 hx, hy, hz;
-    const bool shadowed = traverse<DAG, false>(dag, levels, ray, nullptr, 0, hx, hy, hz);
+#ifdef HDT_TRAVERSE_V1
+    const bool shadowed = traverse_v1<DAG, false>(dag, levels, ray, tab.child, 0, hx, hy, hz);
+#else
+    const bool shadowed = ray_is_tame(ray) ? traverse<DAG, false, true>(dag, levels, ray, tab, 0, hx, hy, hz)
+                                           : traverse<DAG, false, false>(dag, levels, ray, tab, 0, hx, hy, hz);
+#endif
 
     const double vx = __dsub_rn(bo[0], cam.cam[0]), vy = __dsub_rn(bo[1], cam.cam[1]), vz = __dsub_rn(bo[2], cam.cam[2]);
     const double dist = __dsqrt_rn(__fma_rn(vz, vz, __fma_rn(vx, vx, __dmul_rn(vy, vy))));
@@ -218,6 +233,7 @@ struct hdt_ctx {
     u32* frameColors = nullptr;
     u32* pathCache = nullptr;    // pinned, 4 words
     u64 launches = 0;
+    TraverseTables* tables = nullptr;   // device copy of the traversal tables
 
     u64 buffer_pixels() const { return map.world == 1 ? u64(map.width) * map.height : (u64(maxTilesPerRank) << (2 * map.tileLog2)); }
     u32 grid_blocks() const
@@ -357,8 +373,8 @@ void launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
 {
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     if (!grid.x) return;
-    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->paths);
-    else trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->paths);
+    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->paths, c->tables);
+    else trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->paths, c->tables);
     ++c->launches;
 }
 void launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const ColorsParams& prm)
@@ -373,8 +389,8 @@ void launch_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const 
 {
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     if (!grid.x) return;
-    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->colors);
-    else trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->colors);
+    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->colors, c->tables);
+    else trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->colors, c->tables);
     ++c->launches;
 }
 
@@ -418,6 +434,13 @@ int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt
     if (e == cudaSuccess) e = cudaMalloc(&c->hitCounter, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&c->pathCache, 4 * sizeof(u32));
     if (e != cudaSuccess) { hdt_destroy(c); return cuda_fail(e, "hdt_create"); }
+    {
+        TraverseTables host;
+        build_tables(host);
+        e = cudaMalloc(&c->tables, sizeof(TraverseTables));
+        if (e == cudaSuccess) e = cudaMemcpy(c->tables, &host, sizeof(host), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { hdt_destroy(c); return cuda_fail(e, "hdt_create: tables"); }
+    }
     const int rc = configure(c, 0, 1, 6);
     if (rc) { hdt_destroy(c); return rc; }
     *out = c;
@@ -434,6 +457,7 @@ int hdt_destroy(hdt_ctx* c)
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->timer) if (e) cudaEventDestroy(e);
     cudaFree(c->hitCounter);
+    cudaFree(c->tables);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return HDT_OK;

@@ -21,7 +21,7 @@ import numpy as np
 from .camera import CameraView, DAGInfo, trace_params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhashdag_b200.so")
+LIB_PATH = os.environ.get("HDT_LIB", os.path.join(_HERE, "libhashdag_b200.so"))  # HDT_LIB: A/B builds of the same ABI
 
 DAG_BASIC, DAG_HASH = 0, 1
 COLORS_UNCOMPRESSED, COLORS_COMPRESSED, COLORS_ERRORS, COLORS_HASH = 0, 1, 2, 3
