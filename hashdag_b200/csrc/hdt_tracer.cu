@@ -111,6 +111,12 @@ __global__ void __launch_bounds__(kBlockThreads) trace_shadows_kernel(const Came
     auto shade = [&](float lightScale, double distance, double rdx, double rdy, double rdz) {
         const float3 c = rgb888_to_float3(colors[idx]);
         const float lx = __fmul_rn(c.x, lightScale), ly = __fmul_rn(c.y, lightScale), lz = __fmul_rn(c.z, lightScale);
+        if (fd == 0.0f) {
+            // No fog: fogAmount = 1 - exp(-0) = 0 exactly, so lerp(lit, fogColor, 0) = fma(lit, 1, 0*fogColor) = lit
+            // bit for bit (fogColor is finite); the exp/pow of applyFog cannot change the result and are skipped.
+            colors[idx] = float3_to_rgb888(lx, ly, lz);
+            return;
+        }
         const double fogAmount = __dsub_rn(1.0, exp(__dmul_rn(-distance, double(fd))));
         const double dotp = __fma_rn(rdz, double(sp.sunZ), __fma_rn(rdx, double(sp.sunX), __dmul_rn(rdy, double(sp.sunY))));
         const double sunAmount = __dmul_rn(double(1.01f), fmax(dotp, 0.0));

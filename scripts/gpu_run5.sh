@@ -1,0 +1,7 @@
+#!/bin/bash
+OUT=gpurun_out/run6
+mkdir -p $OUT
+exec > >(tee $OUT/log.txt) 2>&1
+echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | grep -v "leaked\|^\s*$\|took\|Creating\|reallocating\|pool size\|page table size\|bloom\|color nodes\|leaves$" | tail -15
+for v in v3 v4; do HDT_LIB=$PWD/build/libhdt_$v.so python scripts/ab_bench.py 13 16 2>&1 | grep '^{\|rror'; done
+HDT_LIB=$PWD/build/libhdt_v4.so python scripts/ab_bench.py 14 16 2>&1 | grep '^{\|rror'
