@@ -218,6 +218,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
     W, H = resolution(args, world)
     hashed = args.dag == "hash"
@@ -264,23 +266,34 @@ def run_ours(args):
     dag_pod, col_pod = dag.pod(), colors.pod()
 
     # ---- multi-GPU gather plumbing ----------------------------------------------------------
+    # Two frames are in flight per rank: frame i's NCCL gather + assembly (queued behind its kernels
+    # on stream i%2) overlaps frame i+1's kernels on the other stream.  No host synchronisation
+    # inside a step; collectives are issued in the same order on every rank.
     gather = None
+    lanes = [tr]
     if world > 1:
-        _, cptr, n_owned, max_tiles = tr.partition_buffers()
-        n = max_tiles << (2 * tile_log2)
-
         class _Mem:
             def __init__(self, ptr, count):
                 self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-        mine = torch.as_tensor(_Mem(cptr, n), device=dev)
-        gathered = torch.empty(world * n, dtype=torch.int32, device=dev) if rank == 0 else None
-        frame = torch.empty(W * H, dtype=torch.int32, device=dev) if rank == 0 else None
+        tr2 = tracer.DAGTracer(True, W, H, args.levels, device=local_rank)
+        tr2.set_partition(rank, world, tile_log2)
+        lanes = [tr, tr2]
+        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        mine, gathered, frames = [], [], []
+        for t_, s_ in zip(lanes, streams):
+            _, cptr, n_owned, max_tiles = t_.partition_buffers()
+            n = max_tiles << (2 * tile_log2)
+            mine.append(torch.as_tensor(_Mem(cptr, n), device=dev))
+            gathered.append(torch.empty(world * n, dtype=torch.int32, device=dev) if rank == 0 else None)
+            frames.append(torch.empty(W * H, dtype=torch.int32, device=dev) if rank == 0 else None)
+            t_.set_stream(s_.cuda_stream)
+        frame = frames[0] if rank == 0 else None
 
-        def gather():
-            dist.gather(mine, list(gathered.chunk(world)) if rank == 0 else None, dst=0)
-            if rank == 0:
-                torch.cuda.current_stream().synchronize()
-                tr.assemble_colors(gathered, frame)
+        def gather(k):
+            with torch.cuda.stream(streams[k]):
+                dist.gather(mine[k], list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
+                if rank == 0:
+                    lanes[k].assemble_colors(gathered[k], frames[k])
     host_frame = torch.empty(W * H, dtype=torch.int32).pin_memory() if rank == 0 else None
 
     def barrier():
@@ -289,10 +302,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device(i):
-        tr.enqueue_frame(params[i % len(params)], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+        k = i % len(lanes)
+        lanes[k].enqueue_frame(params[i % len(params)], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
         if gather:
-            tr.sync()
-            gather()
+            gather(k)
+
+    def sync_all():
+        for t_ in lanes:
+            t_.sync()
 
     # ---- hits per pose (untimed) -------------------------------------------------------------
     hits = []
@@ -308,25 +325,38 @@ def run_ours(args):
     # ---- warm-up ------------------------------------------------------------------------------
     for i in range(args.warmup):
         step_device(i)
-    tr.sync()
+    sync_all()
 
     # ---- timed: K steps, inputs resident, device time, max over ranks ----------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = tr.launch_count()
+    launches0 = sum(t_.launch_count() for t_ in lanes)
     barrier()
     t0 = time.perf_counter()
-    tr.timer_begin()
-    for i in range(args.steps):
-        step_device(args.warmup + i)
-    dev_ms = tr.timer_end()
     if gather:
+        start = torch.cuda.Event(enable_timing=True)
+        start.record()                       # default stream, idle after the barrier
+        for s_ in streams:
+            s_.wait_event(start)
+        for i in range(args.steps):
+            step_device(args.warmup + i)
+        ends = []
+        for s_ in streams:
+            e_ = torch.cuda.Event(enable_timing=True)
+            e_.record(s_)
+            ends.append(e_)
         torch.cuda.synchronize()
+        dev_ms = max(start.elapsed_time(e_) for e_ in ends)
+    else:
+        tr.timer_begin()
+        for i in range(args.steps):
+            step_device(args.warmup + i)
+        dev_ms = tr.timer_end()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    # with a gather in the loop part of the step runs on torch's stream: the barrier-to-barrier wall
-    # clock is then the honest number; single GPU uses the device events on the tracer's stream
-    elapsed_ms = dev_ms if not gather else wall_ms
-    launches = tr.launch_count() - launches0
+    # device events on the streams everything is queued on (kernels, NCCL gather, assembly); the
+    # barrier-to-barrier wall clock is reported beside it
+    elapsed_ms = dev_ms
+    launches = sum(t_.launch_count() for t_ in lanes) - launches0
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -344,9 +374,11 @@ def run_ours(args):
             tr.resolve_frame(p, info, dag, colors, 1.0, 0.0, True, host_frame)
         else:
             tr.resolve_frame(p, info, dag, colors, 1.0, 0.0, True, None)
-            gather()
+            gather(0)
             if rank == 0:
-                host_frame.copy_(frame, non_blocking=False)
+                with torch.cuda.stream(streams[0]):
+                    host_frame.copy_(frame, non_blocking=True)
+                streams[0].synchronize()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     if world > 1:
@@ -382,7 +414,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "setup_s": round(t_build, 1), "scene_build_s": round(scene.build_seconds, 1), "replication_bytes": int(replication_bytes),
-        "timing": "cudaEvents on the tracer stream around K enqueued frames" if not gather else "barrier-to-barrier wall clock incl. NCCL gather + assembly, max over ranks",
+        "timing": "cudaEvents on the tracer stream around K enqueued frames" + ("; two frames in flight, NCCL gather + assembly included, max over ranks" if gather else ""),
+        "wall_ms_per_step": wall_ms / args.steps,
     }
 
     # ---- CPU baseline + algorithmic bytes (bounded sample), roofline -------------------------
@@ -414,9 +447,16 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         dominant = max(gpu_ms_pass, key=lambda k: gpu_ms_pass[k])
+        traffic = None
+        ncu_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(ncu_path):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, same config
+            try:
+                traffic = json.load(open(ncu_path)).get("dram_bytes_per_launch", {}).get(f"trace_{dominant}_kernel<{'HashDagDev' if hashed else 'BasicDagDev'}>")
+            except Exception:
+                traffic = None
         ach = {k: (bytes_pass[k] / (gpu_ms_pass[k] * 1e-3) / 1e9 if gpu_ms_pass[k] > 0 else 0.0) for k in bytes_pass}
         out["roofline"] = {"bound": "hbm", "kernel": f"trace_{dominant}_kernel", "achieved": ach[dominant], "peak": peak, "unit": "GB/s",
-                           "frac": ach[dominant] / peak, "traffic": None, "peak_source": peak_src,
+                           "frac": ach[dominant] / peak, "traffic": traffic, "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": bytes_pass[dominant] / len(sample_ids),
                            "avg_launch_ms": gpu_ms_pass[dominant] / len(sample_ids),
                            "per_pass": {k: {"ms": gpu_ms_pass[k] / len(sample_ids), "algorithmic_GBps": ach[k],

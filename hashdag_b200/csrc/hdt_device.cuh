@@ -428,7 +428,9 @@ __device__ __forceinline__ bool traverse_v1(const DAG& dag, const u32 levels, co
 
 #endif
 
-struct CameraParams { double cam[3], rayMin[3], ddx[3], ddy[3]; };  // TracePathsParams, tracer.h:81-91
+// TracePathsParams (tracer.h:81-91) + the float camera position the kernels would otherwise
+// re-convert from double at every use (make_float3(cameraPosition), tracer.cu:157).
+struct CameraParams { double cam[3], rayMin[3], ddx[3], ddy[3]; float camf[3]; float pad; };
 
 // tracer.cu:158 / :622 with the reference's contraction (see oracle/hdo_oracle.cpp primary_direction)
 __device__ __forceinline__ void primary_direction(const CameraParams& p, u32 px, u32 cameraRow, double& dx, double& dy, double& dz)

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const Camera
     double ddx, ddy, ddz;
     primary_direction(cam, x, map.height - 1 - y, ddx, ddy, ddz);
     Ray ray;
-    ray.ox = __double2float_rn(cam.cam[0]); ray.oy = __double2float_rn(cam.cam[1]); ray.oz = __double2float_rn(cam.cam[2]);
+    ray.ox = cam.camf[0]; ray.oy = cam.camf[1]; ray.oz = cam.camf[2];
     ray.dx = __double2float_rn(ddx); ray.dy = __double2float_rn(ddy); ray.dz = __double2float_rn(ddz);
     ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
     const u32 order = (ray.dx < 0.f ? 4u : 0u) + (ray.dy < 0.f ? 2u : 0u) + (ray.dz < 0.f ? 1u : 0u);
@@ -229,7 +229,8 @@ struct hdt_ctx {
     u32 levels = 0;
     PixelMap map{};
     u32 nOwnedTiles = 0, maxTilesPerRank = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // where work is enqueued (ownStream unless hdt_set_stream)
+    cudaStream_t ownStream = nullptr;
     cudaEvent_t ev[4] = {};
     cudaEvent_t timer[2] = {};
     unsigned long long* hitCounter = nullptr;  // device
@@ -354,7 +355,8 @@ int parse_colors(int kind, const void* pod, size_t size, ColorsDev& out)
 CameraParams make_cam(const double cam[3], const double rmin[3], const double ddx[3], const double ddy[3])
 {
     CameraParams p;
-    for (int k = 0; k < 3; ++k) { p.cam[k] = cam[k]; p.rayMin[k] = rmin[k]; p.ddx[k] = ddx[k]; p.ddy[k] = ddy[k]; }
+    for (int k = 0; k < 3; ++k) { p.cam[k] = cam[k]; p.rayMin[k] = rmin[k]; p.ddx[k] = ddx[k]; p.ddy[k] = ddy[k]; p.camf[k] = float(cam[k]); }
+    p.pad = 0.f;
     return p;
 }
 
@@ -434,7 +436,8 @@ int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt
     hdt_ctx* c = new hdt_ctx();
     c->device = device; c->levels = levels;
     c->map.width = width; c->map.height = height;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking);
+    c->stream = c->ownStream;
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->timer[i]);
     if (e == cudaSuccess) e = cudaMalloc(&c->hitCounter, sizeof(unsigned long long));
@@ -458,13 +461,14 @@ int hdt_destroy(hdt_ctx* c)
     if (!c) return HDT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ownStream) cudaStreamSynchronize(c->ownStream);
     cudaFree(c->paths); cudaFree(c->colors); cudaFree(c->framePaths); cudaFree(c->frameColors);
     if (c->pathCache) cudaFreeHost(c->pathCache);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->timer) if (e) cudaEventDestroy(e);
     cudaFree(c->hitCounter);
     cudaFree(c->tables);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
     delete c;
     return HDT_OK;
 }
@@ -680,8 +684,16 @@ int hdt_assemble_colors(hdt_ctx* c, const uint32_t* gathered_dev, uint32_t* fram
     const dim3 block(32, 8), grid((c->map.width + 31) / 32, (c->map.height + 7) / 8);
     assemble_kernel<u32><<<grid, block, 0, c->stream>>>(gathered_dev, frame_dev, c->map, c->buffer_pixels());
     ++c->launches;
-    HDT_CUDA(cudaStreamSynchronize(c->stream));
     HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+int hdt_set_stream(hdt_ctx* c, void* cuda_stream)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->ownStream;
     return HDT_OK;
 }
 

@@ -34,7 +34,7 @@ EXPORTS = (
     "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_resolve_paths", "hdt_resolve_colors",
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
-    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_apply_ranges", "hdt_launch_count", "hdt_version",
+    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_launch_count", "hdt_version",
 )
 
 
@@ -80,6 +80,7 @@ def load_library():
     lib.hdt_read_colors.argtypes = [C.c_void_p, C.c_void_p]
     lib.hdt_partition_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.hdt_assemble_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hdt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.hdt_apply_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.hdt_launch_count.restype = C.c_uint64
     lib.hdt_launch_count.argtypes = [C.c_void_p]
@@ -360,6 +361,10 @@ class DAGTracer:
 
     def assemble_colors(self, gathered_tensor, frame_tensor=None):
         _check(self._lib.hdt_assemble_colors(self._ctx, gathered_tensor.data_ptr(), 0 if frame_tensor is None else frame_tensor.data_ptr()))
+
+    def set_stream(self, cuda_stream_handle):
+        """Enqueue on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
+        _check(self._lib.hdt_set_stream(self._ctx, cuda_stream_handle))
 
     def launch_count(self) -> int:
         return int(self._lib.hdt_launch_count(self._ctx))

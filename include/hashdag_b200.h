@@ -140,8 +140,13 @@ int hdt_read_colors(hdt_ctx* ctx, uint32_t* host_w_h);
 /* ---- multi-GPU plumbing (the collectives themselves are issued by the host layer) ----------- */
 /* This rank's compact tile buffers (owned tiles back to back, each tile row-major). */
 int hdt_partition_buffers(hdt_ctx* ctx, void** paths_dev, void** colors_dev, uint64_t* n_owned_tiles, uint64_t* max_tiles_per_rank);
-/* Rank 0: scatter `world` gathered compact colour buffers (each max_tiles_per_rank tiles) into the row-major frame. */
+/* Rank 0: scatter `world` gathered compact colour buffers (each max_tiles_per_rank tiles) into the row-major frame.
+ * Asynchronous: enqueued on the tracer's stream, complete after hdt_sync(). */
 int hdt_assemble_colors(hdt_ctx* ctx, const uint32_t* gathered_dev, uint32_t* frame_dev_or_null);
+/* Run the tracer on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL = back to the
+ * context's own stream), so that frames, the NCCL gather and the assembly queue up on one stream
+ * without host synchronisation in between. */
+int hdt_set_stream(hdt_ctx* ctx, void* cuda_stream);
 /* Apply edit-dirtied spans to a replica: dst[range.dst_word + i] = payload[range.src_word + i]. */
 int hdt_apply_ranges(hdt_ctx* ctx, uint32_t* dst_dev, const uint32_t* payload_dev, const hdt_range* ranges_dev, uint32_t n_ranges);
 

@@ -195,6 +195,7 @@ def test_partitioned_render_assembles_to_the_whole_frame(tr):
     t0.set_partition(0, world, tl)
     frame = torch.zeros(H * W, dtype=torch.int32, device="cuda")
     t0.assemble_colors(gathered, frame)
+    t0.sync()
     assert np.array_equal(frame.cpu().numpy().view(np.uint32).reshape(H, W), want_c)
     # host mirror of the same layout
     from hashdag_b200 import partition

@@ -72,3 +72,39 @@ def test_reference_debug_modes_vs_product():
                 t.resolve_colors(dag, col, dbg, lvl)
                 assert np.array_equal(t.read_colors(), rt.read_colors()), f"debug {dbg} level {lvl} dag {dk}"
     t.close()
+
+
+def test_config5_depth16_1080p_basic_vs_hash_with_fog():
+    """BASELINE.json config 5 at full size: depth-16 BasicDAG vs HashDAG of the same scene, compressed
+    colours with every weight width, shadows + fog (density 5), 1920x1080, against the reference
+    kernels.  Paths and colours bit-exact, fogged frame within 1/255, Basic == Hash."""
+    from hashdag_b200 import tracer
+    from conftest import get_scene, scene_cameras
+    if not ref.available(16, 1920, 1080):
+        pytest.skip("oracle/_ref variant not built")
+    W, H = 1920, 1080
+    scene = get_scene(16, 12, seed=5, n_spheres=12)
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    rt = ref.shared(scene, W, H, "config5")
+    t = tracer.DAGTracer(True, W, H, 16)
+    sets = ((0, 1, tracer.BasicDAG.from_scene(scene), tracer.BasicDAGCompressedColors.from_scene(scene)),
+            (1, 3, tracer.HashDAG.from_scene(scene), tracer.HashDAGColors.from_scene(scene)))
+    for pose in scene_cameras(scene, 2, 12)[:3]:
+        frames = []
+        for dk, ck, dag, col in sets:
+            rt.resolve_paths(dk, pose, info)
+            t.resolve_paths(pose, info, dag)
+            rp, p = rt.read_paths(), t.read_paths()
+            assert np.array_equal(p, rp), f"{(p != rp).any(-1).sum()} path pixels differ"
+            rt.resolve_colors(dk, ck)
+            t.resolve_colors(dag, col)
+            assert np.array_equal(t.read_colors(), rt.read_colors())
+            rt.resolve_shadows(dk, pose, info, 1.0, 5.0)
+            t.resolve_shadows(pose, info, dag, 1.0, 5.0)
+            rf, f = rt.read_colors(), t.read_colors()
+            assert gu.channel_diff(f, rf) <= 1
+            assert (f != rf).mean() < 1e-4
+            frames.append((p, f))
+        assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
+        assert frames[0][0][..., :3].any(-1).mean() > 0.3
+    t.close()
