@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-poses", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dag", default="hash", choices=["hash", "basic"])
+    ap.add_argument("--no-beam-prefetch", action="store_true", help="keep the beam kernels of frame n+1 behind all of frame n")
+    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
+                    help="tracer contexts (each with its own streams and frame buffers) the fly-through alternates between")
     return ap.parse_args()
 
 
@@ -163,6 +166,8 @@ def workload_config(args, scene, W, H, world):
         "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, NCCL gather to rank 0",
         "l2_policy": "inputs larger than L2: each step is a different camera pose over a DAG pool >> 126 MB",
         "shadow_bias": 1.0, "fog_density": 0.0,
+        "beam_prefetch": not getattr(args, "no_beam_prefetch", False),
+        "frames_in_flight": 2 if world > 1 else getattr(args, "frames_in_flight", 1),
     }
 
 
@@ -294,6 +299,10 @@ def run_ours(args):
                 dist.gather(mine[k], list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
                 if rank == 0:
                     lanes[k].assemble_colors(gathered[k], frames[k])
+    elif args.frames_in_flight == 2:
+        # single GPU: frame i+1 (second context, own streams and buffers) is enqueued while frame i runs, so the
+        # drain of one kernel overlaps the ramp-up of another instead of leaving SMs idle
+        lanes = [tr, tracer.DAGTracer(True, W, H, args.levels, device=local_rank)]
     host_frame = torch.empty(W * H, dtype=torch.int32).pin_memory() if rank == 0 else None
 
     def barrier():
@@ -322,6 +331,11 @@ def run_ours(args):
         dist.all_reduce(ht)
         hits = ht.tolist()
 
+    # The scene is static during the timed frames, so the ray setup + beam kernels of frame n+1 may run
+    # beside the colours / shadows kernels of frame n (include/hashdag_b200.h, HDT_OPT_BEAM_PREFETCH).
+    for t_ in lanes:
+        t_.set_option(tracer.OPT_BEAM_PREFETCH, 0 if args.no_beam_prefetch else 1)
+
     # ---- warm-up ------------------------------------------------------------------------------
     for i in range(args.warmup):
         step_device(i)
@@ -347,10 +361,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         dev_ms = max(start.elapsed_time(e_) for e_ in ends)
     else:
-        tr.timer_begin()
+        # one event before the first frame on every lane's stream, one after the last: device time of the whole batch
+        for t_ in lanes:
+            t_.timer_begin()
         for i in range(args.steps):
             step_device(args.warmup + i)
-        dev_ms = tr.timer_end()
+        dev_ms = max([t_.timer_end() for t_ in lanes])
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     # device events on the streams everything is queued on (kernels, NCCL gather, assembly); the
@@ -366,6 +382,8 @@ def run_ours(args):
     value = rays / (elapsed_ms * 1e-3) / 1e6
 
     # ---- e2e: public API, host camera in, colour frame out to pinned host memory, every step --
+    for t_ in lanes:
+        t_.set_option(tracer.OPT_BEAM_PREFETCH, 0)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 
+#include "hdt_beam.cuh"
 #include "hdt_colors.cuh"
 #include "hdt_device.cuh"
 
@@ -24,51 +25,134 @@ static_assert(sizeof(hdt_tool_info) == 44, "ToolInfo layout");
 
 namespace {
 
-constexpr u32 kBlockThreads = 256;   // 8 warps, each an 8x4 pixel patch; CTA covers 32x8 pixels
-constexpr u32 kBlockW = 32, kBlockH = 8;
+// A warp is an 8x4-pixel patch (one beam of hdt_beam.cuh); a CTA is kBlockW x kBlockH pixels.
+#ifndef HDT_BLOCK_W
+#define HDT_BLOCK_W 16
+#endif
+#ifndef HDT_BLOCK_H
+#define HDT_BLOCK_H 8
+#endif
+#ifndef HDT_MIN_BLOCKS
+#define HDT_MIN_BLOCKS 1
+#endif
+constexpr u32 kBlockW = HDT_BLOCK_W, kBlockH = HDT_BLOCK_H, kWarpsX = kBlockW / 8;
+constexpr u32 kBlockThreads = kBlockW * kBlockH;
+static_assert(kBlockW % 8 == 0 && kBlockH % 4 == 0 && kBlockW <= 32 && kBlockH <= 32 && kBlockThreads <= 1024, "CTA shape");
 
-// Which pixel does this thread own?  CTAs are numbered tile-major over the tiles this rank owns.
-__device__ __forceinline__ bool thread_pixel(const PixelMap& m, u32& x, u32& y)
+// Which pixel does lane `lane` of warp `warp` of CTA `block` own?  CTAs are numbered tile-major over
+// the screen tiles this rank owns; a warp covers 8x4 pixels (one beam of hdt_beam.cuh).
+__device__ __forceinline__ bool warp_pixel(const PixelMap& m, u32 block, u32 warp, u32 lane, u32& x, u32& y)
 {
     const u32 T = 1u << m.tileLog2, blocksX = T / kBlockW, blocksPerTile = blocksX * (T / kBlockH);
-    const u32 slot = blockIdx.x / blocksPerTile, b = blockIdx.x % blocksPerTile;
+    const u32 slot = block / blocksPerTile, b = block % blocksPerTile;
     const u32 t = m.rank + slot * m.world;
     const u32 tx = t % m.tilesX, ty = t / m.tilesX;
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    x = tx * T + (b % blocksX) * kBlockW + (warp & 3) * 8 + (lane & 7);
-    y = ty * T + (b / blocksX) * kBlockH + (warp >> 2) * 4 + (lane >> 3);
+    x = tx * T + (b % blocksX) * kBlockW + (warp % kWarpsX) * 8 + (lane & 7);
+    y = ty * T + (b / blocksX) * kBlockH + (warp / kWarpsX) * 4 + (lane >> 3);
     return x < m.width && y < m.height;
+}
+__device__ __forceinline__ bool thread_pixel(const PixelMap& m, u32& x, u32& y)
+{
+    return warp_pixel(m, blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, x, y);
+}
+
+// Float ray of pixel (x, cameraRow): tracer.cu:157-165.
+__device__ __forceinline__ void primary_ray(const CameraParams& cam, u32 x, u32 cameraRow, Ray& ray)
+{
+    double ddx, ddy, ddz;
+    primary_direction(cam, x, cameraRow, ddx, ddy, ddz);
+    ray.ox = cam.camf[0]; ray.oy = cam.camf[1]; ray.oz = cam.camf[2];
+    ray.dx = __double2float_rn(ddx); ray.dy = __double2float_rn(ddy); ray.dz = __double2float_rn(ddz);
+    ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
 }
 
 // ---------------------------------------------------------------------------------------------
 // trace_paths (tracer.cu:145-252).  Output pixel row r holds camera row height-1-r (:251).
+// Three kernels: ray setup (one thread per pixel), beam pre-pass (one thread per 8x4 tile, hdt_beam.cuh,
+// concurrent with) the per-ray traversal.
 // ---------------------------------------------------------------------------------------------
+#ifdef HDT_BEAM_DEBUG
+__device__ u32 g_beamDebug[8];   // warps of the per-ray kernels by the beam status they saw: [0..3] paths, [4..7] shadows
+#endif
+
+// A frame of rays as three planes of floats, indexed like the paths buffer.
+struct RayPlanes {
+    float* __restrict__ base; u64 n;
+    __device__ __forceinline__ void store(u64 i, float a, float b, float c) const { base[i] = a; base[n + i] = b; base[2 * n + i] = c; }
+    __device__ __forceinline__ void load(u64 i, float& a, float& b, float& c) const { a = base[i]; b = base[n + i]; c = base[2 * n + i]; }
+};
+
+__device__ __forceinline__ u32 ray_order(const Ray& r) { return (r.dx < 0.f ? 4u : 0u) + (r.dy < 0.f ? 2u : 0u) + (r.dz < 0.f ? 1u : 0u); }
+
+// Ray setup: the double-precision normalisation of tracer.cu:158 once per pixel; the float direction
+// goes to `dirs` for the per-ray kernel, its range over each 8x4 tile to `seeds` for the beam kernel.
+__global__ void __launch_bounds__(kBlockThreads) setup_paths_kernel(const CameraParams cam, const PixelMap map, const RayPlanes dirs,
+                                                                    BeamSeed* __restrict__ seeds)
+{
+    u32 x, y;
+    const bool active = thread_pixel(map, x, y);
+    Ray ray;
+    primary_ray(cam, active ? x : 0, active ? map.height - 1 - y : 0, ray);
+    if (active) dirs.store(map.index(x, y), ray.dx, ray.dy, ray.dz);
+    const float d[3] = { ray.dx, ray.dy, ray.dz };
+    write_seed(seeds + (blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)), d, active, ray_is_tame(ray), ray_order(ray));
+}
+
+// Beam pre-pass: one thread per tile walks the DFS with interval masks.
 template <class DAG>
-__global__ void __launch_bounds__(kBlockThreads) trace_paths_kernel(const CameraParams cam, const DAG dag, const u32 levels, const PixelMap map,
-                                                                    uint4* __restrict__ paths, const TraverseTables* __restrict__ tables)
+__global__ void __launch_bounds__(32) beam_paths_kernel(const CameraParams cam, const DAG dag, const u32 levels, const BeamSeed* __restrict__ seeds,
+                                                        BeamState* __restrict__ beams, const u32 nBeams, const u32 maxVisits, const u32 tag,
+                                                        const TraverseTables* __restrict__ tables)
 {
     __shared__ TraverseTables tab;
     load_tables(tab, tables);
     __syncthreads();
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nBeams) return;
+    BeamState* out = beams + g;
+    const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(seeds + g)), s1 = __ldg(reinterpret_cast<const uint4*>(seeds + g) + 1);
+    BeamRays br;
+    br.d[0] = { __uint_as_float(s0.x), __uint_as_float(s1.x) };
+    br.d[1] = { __uint_as_float(s0.y), __uint_as_float(s1.y) };
+    br.d[2] = { __uint_as_float(s0.z), __uint_as_float(s1.z) };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) br.o[k] = { cam.camf[k], cam.camf[k] };
+    if (!s0.w || !finish_beam(br)) { store_release(&out->status, (tag << 2) | kBeamNone); return; }
+    beam_traverse<DAG, true>(dag, levels, br, tab, s1.w, maxVisits, tag, out);
+}
+
+template <class DAG>
+__global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_paths_kernel(const CameraParams cam, const DAG dag, const u32 levels, const PixelMap map,
+                                                                    const RayPlanes dirs, uint4* __restrict__ paths,
+                                                                    const TraverseTables* __restrict__ tables, const BeamState* __restrict__ beams,
+                                                                    const u32 tag)
+{
+    __shared__ TraverseTables tab;
+    load_tables(tab, tables);
+    const BeamState* bs = beams ? beams + (blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)) : nullptr;
+    const u32 status = beam_status(bs, tag);   // whole warp, before anybody leaves
+#ifdef HDT_BEAM_DEBUG
+    if (beams && (threadIdx.x & 31) == 0) atomicAdd(&g_beamDebug[status], 1u);
+#endif
+    __syncthreads();
     u32 x, y;
     if (!thread_pixel(map, x, y)) return;
-
-    double ddx, ddy, ddz;
-    primary_direction(cam, x, map.height - 1 - y, ddx, ddy, ddz);
-    Ray ray;
-    ray.ox = cam.camf[0]; ray.oy = cam.camf[1]; ray.oz = cam.camf[2];
-    ray.dx = __double2float_rn(ddx); ray.dy = __double2float_rn(ddy); ray.dz = __double2float_rn(ddz);
-    ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
-    const u32 order = (ray.dx < 0.f ? 4u : 0u) + (ray.dy < 0.f ? 2u : 0u) + (ray.dz < 0.f ? 1u : 0u);
+    const u64 idx = map.index(x, y);
 
     u32 px, py, pz;
-#ifdef HDT_TRAVERSE_V1
-    traverse_v1<DAG, true>(dag, levels, ray, tab.child, order, px, py, pz);
-#else
-    if (ray_is_tame(ray)) traverse<DAG, true, true>(dag, levels, ray, tab, order, px, py, pz);
-    else traverse<DAG, true, false>(dag, levels, ray, tab, order, px, py, pz);
-#endif
-    paths[map.index(x, y)] = make_uint4(px, py, pz, 0);
+    if (status == kBeamHit) { px = __ldcg(&bs->level); py = __ldcg(&bs->pending); pz = __ldcg(&bs->handle); }
+    else if (status == kBeamMiss) px = py = pz = 0;
+    else {
+        Ray ray;
+        ray.ox = cam.camf[0]; ray.oy = cam.camf[1]; ray.oz = cam.camf[2];
+        dirs.load(idx, ray.dx, ray.dy, ray.dz);
+        ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
+        const u32 order = ray_order(ray);
+        if (status == kBeamResume) traverse_from<DAG, true>(dag, levels, ray, tab, order, bs, px, py, pz);
+        else if (ray_is_tame(ray)) traverse<DAG, true, true>(dag, levels, ray, tab, order, px, py, pz);
+        else traverse<DAG, true, false>(dag, levels, ray, tab, order, px, py, pz);
+    }
+    paths[idx] = make_uint4(px, py, pz, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -90,44 +174,11 @@ __global__ void __launch_bounds__(kBlockThreads) trace_colors_kernel(const DAG d
 // ---------------------------------------------------------------------------------------------
 struct ShadowParams { float shadowBias, fogDensity; float sunX, sunY, sunZ; };
 
-template <class DAG>
-__global__ void __launch_bounds__(kBlockThreads) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
-                                                                      const PixelMap map, const uint4* __restrict__ paths, u32* __restrict__ colors,
-                                                                      const TraverseTables* __restrict__ tables)
+// Shadow ray of a hit pixel (tracer.cu:622-655): origin = exact hit point of the primary ray on the
+// voxel [p, p+1] (ray_box_intersection, tracer.cu:574-587, in double) + shadowBias * sun.
+__device__ __forceinline__ void shadow_ray(const CameraParams& cam, const ShadowParams& sp, const uint4 p, const double dirx, const double diry,
+                                           const double dirz, Ray& ray)
 {
-    __shared__ TraverseTables tab;
-    load_tables(tab, tables);
-    __syncthreads();
-    u32 x, y;
-    if (!thread_pixel(map, x, y)) return;
-    const u64 idx = map.index(x, y);
-    const uint4 p = paths[idx];
-
-    double dirx, diry, dirz;
-    primary_direction(cam, x, map.height - 1 - y, dirx, diry, dirz);   // the row flip of tracer.cu:622 cancels the one of :251
-
-    // setColor (tracer.cu:604-619) + applyFog (:551-572); contraction as in the reference PTX
-    const float fd = __fmul_rn(sp.fogDensity, 0.00001f);
-    auto shade = [&](float lightScale, double distance, double rdx, double rdy, double rdz) {
-        const float3 c = rgb888_to_float3(colors[idx]);
-        const float lx = __fmul_rn(c.x, lightScale), ly = __fmul_rn(c.y, lightScale), lz = __fmul_rn(c.z, lightScale);
-        if (fd == 0.0f) {
-            // No fog: fogAmount = 1 - exp(-0) = 0 exactly, so lerp(lit, fogColor, 0) = fma(lit, 1, 0*fogColor) = lit
-            // bit for bit (fogColor is finite); the exp/pow of applyFog cannot change the result and are skipped.
-            colors[idx] = float3_to_rgb888(lx, ly, lz);
-            return;
-        }
-        const double fogAmount = __dsub_rn(1.0, exp(__dmul_rn(-distance, double(fd))));
-        const double dotp = __fma_rn(rdz, double(sp.sunZ), __fma_rn(rdx, double(sp.sunX), __dmul_rn(rdy, double(sp.sunY))));
-        const double sunAmount = __dmul_rn(double(1.01f), fmax(dotp, 0.0));
-        const float pw = __double2float_rn(pow(sunAmount, 30.0)), q = __fsub_rn(1.f, pw);
-        const float fx = __fmaf_rn(q, __fdiv_rn(187.f, 255.f), pw), fy = __fmaf_rn(q, __fdiv_rn(242.f, 255.f), pw), fz = __fmaf_rn(q, __fdiv_rn(250.f, 255.f), pw);
-        const float g = clampf(__double2float_rn(fogAmount), 0.f, 1.f), h = __fsub_rn(1.f, g);
-        colors[idx] = float3_to_rgb888(__fmaf_rn(lx, h, __fmul_rn(g, fx)), __fmaf_rn(ly, h, __fmul_rn(g, fy)), __fmaf_rn(lz, h, __fmul_rn(g, fz)));
-    };
-    if ((p.x | p.y | p.z) == 0) { shade(1.0f, 1e9, dirx, diry, dirz); return; }
-
-    // ray_box_intersection (tracer.cu:574-587) against the voxel [p, p+1]
     const double bo[3] = { double(__uint2float_rn(p.x)), double(__uint2float_rn(p.y)), double(__uint2float_rn(p.z)) };
     const double dv[3] = { dirx, diry, dirz };
     double rm[3];
@@ -138,23 +189,124 @@ __global__ void __launch_bounds__(kBlockThreads) trace_shadows_kernel(const Came
         rm[k] = (t0 < t1) ? t0 : t1;
     }
     const double maxmin = fmax(fmax(rm[0], rm[1]), rm[2]);
-    Ray ray;
     ray.ox = __fmaf_rn(sp.shadowBias, sp.sunX, __double2float_rn(__fma_rn(dv[0], maxmin, cam.cam[0])));
     ray.oy = __fmaf_rn(sp.shadowBias, sp.sunY, __double2float_rn(__fma_rn(dv[1], maxmin, cam.cam[1])));
     ray.oz = __fmaf_rn(sp.shadowBias, sp.sunZ, __double2float_rn(__fma_rn(dv[2], maxmin, cam.cam[2])));
     ray.dx = sp.sunX; ray.dy = sp.sunY; ray.dz = sp.sunZ;
     ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
-    u32 hx, hy, hz;
-#ifdef HDT_TRAVERSE_V1
-    const bool shadowed = traverse_v1<DAG, false>(dag, levels, ray, tab.child, 0, hx, hy, hz);
-#else
-    const bool shadowed = ray_is_tame(ray) ? traverse<DAG, false, true>(dag, levels, ray, tab, 0, hx, hy, hz)
-                                           : traverse<DAG, false, false>(dag, levels, ray, tab, 0, hx, hy, hz);
-#endif
+}
 
-    const double vx = __dsub_rn(bo[0], cam.cam[0]), vy = __dsub_rn(bo[1], cam.cam[1]), vz = __dsub_rn(bo[2], cam.cam[2]);
-    const double dist = __dsqrt_rn(__fma_rn(vz, vz, __fma_rn(vx, vx, __dmul_rn(vy, vy))));
-    shade(shadowed ? 0.5f : 1.0f, dist, __ddiv_rn(vx, dist), __ddiv_rn(vy, dist), __ddiv_rn(vz, dist));
+// Ray setup of trace_shadows, once per pixel: the shadow ray's origin goes to `origins` (hit pixels
+// only), its range over each 8x4 tile to `seeds`.
+__global__ void __launch_bounds__(kBlockThreads) setup_shadows_kernel(const CameraParams cam, const ShadowParams sp, const PixelMap map,
+                                                                      const uint4* __restrict__ paths, const RayPlanes origins,
+                                                                      BeamSeed* __restrict__ seeds)
+{
+    u32 x, y;
+    bool active = thread_pixel(map, x, y);
+    u64 idx = 0;
+    uint4 p = make_uint4(0, 0, 0, 0);
+    if (active) { idx = map.index(x, y); p = paths[idx]; }
+    active = active && (p.x | p.y | p.z) != 0;
+    Ray ray;
+    ray.ox = ray.oy = ray.oz = 0.f; ray.dx = ray.dy = ray.dz = ray.ix = ray.iy = ray.iz = 1.f;
+    if (active) {
+        double dirx, diry, dirz;
+        primary_direction(cam, x, map.height - 1 - y, dirx, diry, dirz);   // the row flip of tracer.cu:622 cancels the one of :251
+        shadow_ray(cam, sp, p, dirx, diry, dirz, ray);
+        origins.store(idx, ray.ox, ray.oy, ray.oz);
+    }
+    const float o[3] = { ray.ox, ray.oy, ray.oz };
+    write_seed(seeds + (blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)), o, active, ray_is_tame(ray), 0);
+}
+
+// Beam pre-pass of trace_shadows: the shadow rays of a tile share the direction; their origins span a box.
+template <class DAG>
+__global__ void __launch_bounds__(32) beam_shadows_kernel(const ShadowParams sp, const DAG dag, const u32 levels, const BeamSeed* __restrict__ seeds,
+                                                          BeamState* __restrict__ beams, const u32 nBeams, const u32 maxVisits, const u32 tag,
+                                                          const TraverseTables* __restrict__ tables)
+{
+    __shared__ TraverseTables tab;
+    load_tables(tab, tables);
+    __syncthreads();
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nBeams) return;
+    BeamState* out = beams + g;
+    const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(seeds + g)), s1 = __ldg(reinterpret_cast<const uint4*>(seeds + g) + 1);
+    BeamRays br;
+    br.o[0] = { __uint_as_float(s0.x), __uint_as_float(s1.x) };
+    br.o[1] = { __uint_as_float(s0.y), __uint_as_float(s1.y) };
+    br.o[2] = { __uint_as_float(s0.z), __uint_as_float(s1.z) };
+    br.d[0] = { sp.sunX, sp.sunX }; br.d[1] = { sp.sunY, sp.sunY }; br.d[2] = { sp.sunZ, sp.sunZ };
+    if (!s0.w || !finish_beam(br)) { store_release(&out->status, (tag << 2) | kBeamNone); return; }
+    beam_traverse<DAG, false>(dag, levels, br, tab, 0, maxVisits, tag, out);
+}
+
+template <class DAG>
+__global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
+                                                                      const PixelMap map, const uint4* __restrict__ paths, const RayPlanes origins,
+                                                                      u32* __restrict__ colors, const TraverseTables* __restrict__ tables,
+                                                                      const BeamState* __restrict__ beams, const u32 tag)
+{
+    __shared__ TraverseTables tab;
+    load_tables(tab, tables);
+    const BeamState* bs = beams ? beams + (blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)) : nullptr;
+    const u32 status = beam_status(bs, tag);   // whole warp, before anybody leaves
+#ifdef HDT_BEAM_DEBUG
+    if (beams && (threadIdx.x & 31) == 0) atomicAdd(&g_beamDebug[4 + status], 1u);
+#endif
+    __syncthreads();
+    u32 x, y;
+    if (!thread_pixel(map, x, y)) return;
+    const u64 idx = map.index(x, y);
+    const uint4 p = paths[idx];
+
+    // setColor (tracer.cu:604-619) + applyFog (:551-572); contraction as in the reference PTX.
+    // hit == false: sky pixel, distance 1e9 along the primary direction (tracer.cu:644-648).
+    const float fd = __fmul_rn(sp.fogDensity, 0.00001f);
+    auto shade = [&](float lightScale, bool hit) {
+        const float3 c = rgb888_to_float3(colors[idx]);
+        const float lx = __fmul_rn(c.x, lightScale), ly = __fmul_rn(c.y, lightScale), lz = __fmul_rn(c.z, lightScale);
+        if (fd == 0.0f) {
+            // No fog: fogAmount = 1 - exp(-0) = 0 exactly, so lerp(lit, fogColor, 0) = fma(lit, 1, 0*fogColor) = lit
+            // bit for bit (fogColor is finite); distance, direction, exp and pow of applyFog cannot change the
+            // result and are not computed.
+            colors[idx] = float3_to_rgb888(lx, ly, lz);
+            return;
+        }
+        double distance = 1e9, rdx, rdy, rdz;
+        if (hit) {
+            const double vx = __dsub_rn(double(__uint2float_rn(p.x)), cam.cam[0]), vy = __dsub_rn(double(__uint2float_rn(p.y)), cam.cam[1]),
+                         vz = __dsub_rn(double(__uint2float_rn(p.z)), cam.cam[2]);
+            distance = __dsqrt_rn(__fma_rn(vz, vz, __fma_rn(vx, vx, __dmul_rn(vy, vy))));
+            rdx = __ddiv_rn(vx, distance); rdy = __ddiv_rn(vy, distance); rdz = __ddiv_rn(vz, distance);
+        } else {
+            primary_direction(cam, x, map.height - 1 - y, rdx, rdy, rdz);
+        }
+        const double fogAmount = __dsub_rn(1.0, exp(__dmul_rn(-distance, double(fd))));
+        const double dotp = __fma_rn(rdz, double(sp.sunZ), __fma_rn(rdx, double(sp.sunX), __dmul_rn(rdy, double(sp.sunY))));
+        const double sunAmount = __dmul_rn(double(1.01f), fmax(dotp, 0.0));
+        const float pw = __double2float_rn(pow(sunAmount, 30.0)), q = __fsub_rn(1.f, pw);
+        const float fx = __fmaf_rn(q, __fdiv_rn(187.f, 255.f), pw), fy = __fmaf_rn(q, __fdiv_rn(242.f, 255.f), pw), fz = __fmaf_rn(q, __fdiv_rn(250.f, 255.f), pw);
+        const float g = clampf(__double2float_rn(fogAmount), 0.f, 1.f), h = __fsub_rn(1.f, g);
+        colors[idx] = float3_to_rgb888(__fmaf_rn(lx, h, __fmul_rn(g, fx)), __fmaf_rn(ly, h, __fmul_rn(g, fy)), __fmaf_rn(lz, h, __fmul_rn(g, fz)));
+    };
+    if ((p.x | p.y | p.z) == 0) { shade(1.0f, false); return; }
+
+    bool shadowed;
+    if (status == kBeamHit) shadowed = true;
+    else if (status == kBeamMiss) shadowed = false;
+    else {
+        Ray ray;
+        origins.load(idx, ray.ox, ray.oy, ray.oz);
+        ray.dx = sp.sunX; ray.dy = sp.sunY; ray.dz = sp.sunZ;
+        ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
+        u32 hx, hy, hz;
+        if (status == kBeamResume) shadowed = traverse_from<DAG, false>(dag, levels, ray, tab, 0, bs, hx, hy, hz);
+        else shadowed = ray_is_tame(ray) ? traverse<DAG, false, true>(dag, levels, ray, tab, 0, hx, hy, hz)
+                                         : traverse<DAG, false, false>(dag, levels, ray, tab, 0, hx, hy, hz);
+    }
+    shade(shadowed ? 0.5f : 1.0f, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,6 +345,16 @@ __global__ void count_hits_kernel(const uint4* __restrict__ paths, u64 n, unsign
     }
     local = __reduce_add_sync(0xFFFFFFFFu, local);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
+// Histogram of the last beam pre-pass: out[status] += 1, out[4] += level at which resuming tiles hand over.
+__global__ void beam_stats_kernel(const BeamState* __restrict__ beams, u32 n, unsigned long long* __restrict__ out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 st = beams[i].status & 3u;
+    atomicAdd(out + st, 1ull);
+    if (st == kBeamResume) atomicAdd(out + 4, (unsigned long long)beams[i].level);
 }
 
 __global__ void apply_ranges_kernel(u32* __restrict__ dst, const u32* __restrict__ payload, const hdt_range* __restrict__ ranges, u32 nRanges)
@@ -241,6 +403,23 @@ struct hdt_ctx {
     u32* pathCache = nullptr;    // pinned, 4 words
     u64 launches = 0;
     TraverseTables* tables = nullptr;   // device copy of the traversal tables
+    // Beam pre-pass (hdt_beam.cuh): per pass (0 = paths, 1 = shadows) one BeamState + BeamSeed per 8x4-pixel
+    // tile (= warp of the per-ray kernels) and three float planes of per-pixel ray data (directions / origins).
+    BeamState* beams[2] = {};
+    BeamSeed* seeds[2] = {};
+    float* rays[2] = {};
+    cudaStream_t side = nullptr;        // beam kernels run here, concurrently with the per-ray kernels
+    cudaEvent_t fork[2] = {}, setupDone[2] = {}, join[2] = {}, traceDone[2] = {};   // per pass; traceDone[0] also gates the prefetch
+    bool useBeams = true;
+    bool beamPrefetch = false;
+    bool beamSerial = false;            // diagnostics: per-ray kernels wait for the beam kernel
+    u32 beamMaxVisits = 32;
+    u32 beamTag = 0;                    // bumped per beam launch; per-ray kernels ignore states of other launches
+    int lastBeamPass = 0;
+
+    RayPlanes ray_planes(int pass) const { return RayPlanes{ rays[pass], buffer_pixels() }; }
+
+    u32 n_beams() const { return grid_blocks() * (kBlockThreads / 32); }
 
     u64 buffer_pixels() const { return map.world == 1 ? u64(map.width) * map.height : (u64(maxTilesPerRank) << (2 * map.tileLog2)); }
     u32 grid_blocks() const
@@ -256,10 +435,16 @@ int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
 {
     if (world == 0 || rank >= world || tileLog2 < 5 || tileLog2 > 10) return fail(HDT_ERR_ARG, "bad partition");
     HDT_CUDA(cudaSetDevice(c->device));
+    if (c->side) HDT_CUDA(cudaStreamSynchronize(c->side));
     if (c->paths) { cudaFree(c->paths); c->paths = nullptr; }
     if (c->colors) { cudaFree(c->colors); c->colors = nullptr; }
     if (c->framePaths) { cudaFree(c->framePaths); c->framePaths = nullptr; }
     if (c->frameColors) { cudaFree(c->frameColors); c->frameColors = nullptr; }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->beams[i]); c->beams[i] = nullptr;
+        cudaFree(c->seeds[i]); c->seeds[i] = nullptr;
+        cudaFree(c->rays[i]); c->rays[i] = nullptr;
+    }
     PixelMap& m = c->map;
     m.tileLog2 = tileLog2; m.world = world; m.rank = rank;
     const u32 T = 1u << tileLog2;
@@ -270,6 +455,12 @@ int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
     const u64 n = c->buffer_pixels();
     HDT_CUDA(cudaMalloc(&c->paths, n * sizeof(uint4)));
     HDT_CUDA(cudaMalloc(&c->colors, n * sizeof(u32)));
+    for (int i = 0; i < 2 && c->n_beams(); ++i) {
+        HDT_CUDA(cudaMalloc(&c->beams[i], size_t(c->n_beams()) * sizeof(BeamState)));
+        HDT_CUDA(cudaMemsetAsync(c->beams[i], 0xFF, size_t(c->n_beams()) * sizeof(BeamState), c->stream));   // no launch has tag 2^30-1
+        HDT_CUDA(cudaMalloc(&c->seeds[i], size_t(c->n_beams()) * sizeof(BeamSeed)));
+        HDT_CUDA(cudaMalloc(&c->rays[i], n * 3 * sizeof(float)));
+    }
     HDT_CUDA(cudaMemsetAsync(c->paths, 0, n * sizeof(uint4), c->stream));
     HDT_CUDA(cudaMemsetAsync(c->colors, 0, n * sizeof(u32), c->stream));
     HDT_CUDA(cudaStreamSynchronize(c->stream));
@@ -377,13 +568,45 @@ ShadowParams make_shadow(float bias, float fog)
     return sp;
 }
 
+// Launch tags run through 0 .. 2^30-2; the state buffers are initialised with 2^30-1.
+u32 next_beam_tag(hdt_ctx* c) { return c->beamTag = (c->beamTag + 1) % 0x3FFFFFFFu; }
+
 void launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
 {
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     if (!grid.x) return;
-    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->paths, c->tables);
-    else trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->paths, c->tables);
+    // Ray setup and beams on the side stream.  Normally they are ordered after everything enqueued on the
+    // main stream so far.  With HDT_OPT_BEAM_PREFETCH the caller promises that the DAG is not modified by
+    // work queued on the tracer's stream, and they only wait for the previous paths kernel (the last
+    // reader of their buffers): enqueued right behind the previous frame, they then run beside its
+    // colours / shadows kernels, and the per-ray kernel below finds every beam finished.
+    cudaEventRecord(c->fork[0], c->stream);
+    if (c->beamPrefetch) cudaStreamWaitEvent(c->side, c->traceDone[0], 0);
+    else {
+        cudaStreamWaitEvent(c->side, c->fork[0], 0);
+    }
+    setup_paths_kernel<<<grid, block, 0, c->side>>>(cam, c->map, c->ray_planes(0), c->seeds[0]);
+    cudaEventRecord(c->setupDone[0], c->side);
     ++c->launches;
+    const BeamState* beams = nullptr;
+    u32 tag = 0;
+    if (c->useBeams) {
+        beams = c->beams[0];
+        tag = next_beam_tag(c);
+        const u32 nb = c->n_beams();
+        const dim3 g((nb + 31) / 32), b(32);
+        if (d.kind == HDT_DAG_BASIC) beam_paths_kernel<BasicDagDev><<<g, b, 0, c->side>>>(cam, d.basic, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
+        else beam_paths_kernel<HashDagDev><<<g, b, 0, c->side>>>(cam, d.hash, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
+        ++c->launches;
+        c->lastBeamPass = 0;
+    }
+    cudaEventRecord(c->join[0], c->side);
+    cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[0] : c->setupDone[0], 0);   // the directions
+    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
+    else trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
+    cudaEventRecord(c->traceDone[0], c->stream);
+    ++c->launches;
+    cudaStreamWaitEvent(c->stream, c->join[0], 0);   // a synchronisation of the main stream covers the beam kernel too
 }
 void launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const ColorsParams& prm)
 {
@@ -393,13 +616,48 @@ void launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const Colo
     else trace_colors_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(d.hash, col, c->levels, prm, c->map, c->paths, c->colors);
     ++c->launches;
 }
+// trace_shadows in two halves so that a whole-frame call can enqueue the first one (ray setup + beams, which
+// only need the paths frame; side stream) before the colours kernel and the second one after it.
+struct ShadowPrep { const BeamState* beams = nullptr; u32 tag = 0; bool valid = false; };
+
+ShadowPrep prepare_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp)
+{
+    ShadowPrep prep;
+    const dim3 grid(c->grid_blocks()), block(kBlockThreads);
+    if (!grid.x) return prep;
+    prep.valid = true;
+    cudaEventRecord(c->fork[1], c->stream);
+    cudaStreamWaitEvent(c->side, c->fork[1], 0);
+    setup_shadows_kernel<<<grid, block, 0, c->side>>>(cam, sp, c->map, c->paths, c->ray_planes(1), c->seeds[1]);
+    cudaEventRecord(c->setupDone[1], c->side);
+    ++c->launches;
+    if (c->useBeams) {
+        prep.beams = c->beams[1];
+        prep.tag = next_beam_tag(c);
+        const u32 nb = c->n_beams();
+        const dim3 g((nb + 31) / 32), b(32);
+        if (d.kind == HDT_DAG_BASIC) beam_shadows_kernel<BasicDagDev><<<g, b, 0, c->side>>>(sp, d.basic, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
+        else beam_shadows_kernel<HashDagDev><<<g, b, 0, c->side>>>(sp, d.hash, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
+        ++c->launches;
+        c->lastBeamPass = 1;
+    }
+    cudaEventRecord(c->join[1], c->side);
+    return prep;
+}
+void finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp, const ShadowPrep& prep)
+{
+    if (!prep.valid) return;
+    const dim3 grid(c->grid_blocks()), block(kBlockThreads);
+    cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[1] : c->setupDone[1], 0);   // the origins
+    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
+    else trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
+    cudaEventRecord(c->traceDone[1], c->stream);
+    ++c->launches;
+    cudaStreamWaitEvent(c->stream, c->join[1], 0);
+}
 void launch_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp)
 {
-    const dim3 grid(c->grid_blocks()), block(kBlockThreads);
-    if (!grid.x) return;
-    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->colors, c->tables);
-    else trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->colors, c->tables);
-    ++c->launches;
+    finish_shadows(c, d, cam, sp, prepare_shadows(c, d, cam, sp));
 }
 
 int check_combo(int dagKind, int colorsKind)
@@ -436,10 +694,22 @@ int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt
     hdt_ctx* c = new hdt_ctx();
     c->device = device; c->levels = levels;
     c->map.width = width; c->map.height = height;
+    if (const char* env = getenv("HDT_BEAMS")) c->useBeams = atoi(env) != 0;
+    if (const char* env = getenv("HDT_BEAM_PREFETCH")) c->beamPrefetch = atoi(env) != 0;
+    if (const char* env = getenv("HDT_BEAM_MAX_VISITS")) c->beamMaxVisits = u32(atoi(env) > 0 ? atoi(env) : 1);
     cudaError_t e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking);
     c->stream = c->ownStream;
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->timer[i]);
+    {
+        int lo = 0, hi = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);   // hi = greatest priority
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->fork[i]);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->join[i]);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->setupDone[i]);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->traceDone[i]);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&c->hitCounter, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&c->pathCache, 4 * sizeof(u32));
     if (e != cudaSuccess) { hdt_destroy(c); return cuda_fail(e, "hdt_create"); }
@@ -468,9 +738,28 @@ int hdt_destroy(hdt_ctx* c)
     for (auto& e : c->timer) if (e) cudaEventDestroy(e);
     cudaFree(c->hitCounter);
     cudaFree(c->tables);
+    if (c->side) cudaStreamSynchronize(c->side);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->beams[i]); cudaFree(c->seeds[i]); cudaFree(c->rays[i]);
+        if (c->fork[i]) cudaEventDestroy(c->fork[i]);
+        if (c->join[i]) cudaEventDestroy(c->join[i]);
+        if (c->setupDone[i]) cudaEventDestroy(c->setupDone[i]);
+        if (c->traceDone[i]) cudaEventDestroy(c->traceDone[i]);
+    }
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
     delete c;
     return HDT_OK;
+}
+
+int hdt_set_option(hdt_ctx* c, int option, int value)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    if (option == HDT_OPT_BEAMS) { c->useBeams = value != 0; return HDT_OK; }
+    if (option == HDT_OPT_BEAM_PREFETCH) { c->beamPrefetch = value != 0; return HDT_OK; }
+    if (option == HDT_OPT_BEAM_SERIAL) { c->beamSerial = value != 0; return HDT_OK; }
+    if (option == HDT_OPT_BEAM_MAX_VISITS) { if (value < 1) return fail(HDT_ERR_ARG, "beam visit cap must be >= 1"); c->beamMaxVisits = u32(value); return HDT_OK; }
+    return fail(HDT_ERR_ARG, "unknown option");
 }
 
 int hdt_set_partition(hdt_ctx* c, uint32_t rank, uint32_t world, uint32_t tile_log2)
@@ -540,9 +829,13 @@ static int enqueue_frame(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t d
     if (events) HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
     launch_paths(c, d, cp);
     if (events) HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    // the shadow pass' ray setup and beams only need the paths frame: start them beside the colours kernel
+    const ShadowParams sp = make_shadow(shadow_bias, fog_density);
+    ShadowPrep prep;
+    if (with_shadows) prep = prepare_shadows(c, d, cp, sp);
     launch_colors(c, d, col, prm);
     if (events) HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    if (with_shadows) launch_shadows(c, d, cp, make_shadow(shadow_bias, fog_density));
+    if (with_shadows) finish_shadows(c, d, cp, sp, prep);
     if (events) HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
     if (host_colors)
         HDT_CUDA(cudaMemcpyAsync(host_colors, c->colors, u64(c->map.width) * c->map.height * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
@@ -614,6 +907,50 @@ int hdt_count_hits(hdt_ctx* c, uint64_t* n_hits)
     HDT_CUDA(cudaStreamSynchronize(c->stream));
     HDT_CUDA(cudaGetLastError());
     *n_hits = v;
+    return HDT_OK;
+}
+
+#ifdef HDT_BEAM_DEBUG
+extern "C" int hdt_debug_beam_counters(uint32_t out[8], int reset)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_beamDebug, 8 * sizeof(u32)) != cudaSuccess) return 1;
+    if (reset) { const u32 z[8] = {}; cudaMemcpyToSymbol(g_beamDebug, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
+int hdt_beam_stats(hdt_ctx* c, uint64_t out[5])
+{
+    if (!c || !out) return fail(HDT_ERR_ARG, "null argument");
+    for (int i = 0; i < 5; ++i) out[i] = 0;
+    const u32 n = c->n_beams();
+    const BeamState* beams = c->beams[c->lastBeamPass];
+    if (!beams || !n) return HDT_OK;
+    HDT_CUDA(cudaSetDevice(c->device));
+    unsigned long long* dev = nullptr;
+    HDT_CUDA(cudaMalloc(&dev, 5 * sizeof(unsigned long long)));
+    cudaMemsetAsync(dev, 0, 5 * sizeof(unsigned long long), c->stream);
+    beam_stats_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(beams, n, dev);
+    ++c->launches;
+    unsigned long long host[5] = {};
+    cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return cuda_fail(e, "hdt_beam_stats");
+    for (int i = 0; i < 5; ++i) out[i] = host[i];
+    return HDT_OK;
+}
+
+int hdt_pass_timeline(hdt_ctx* c, int pass, float ms[3])
+{
+    if (!c || !ms || pass < 0 || pass > 1) return fail(HDT_ERR_ARG, "bad argument");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->side));
+    HDT_CUDA(cudaEventElapsedTime(&ms[0], c->fork[pass], c->setupDone[pass]));
+    HDT_CUDA(cudaEventElapsedTime(&ms[1], c->fork[pass], c->join[pass]));
+    HDT_CUDA(cudaEventElapsedTime(&ms[2], c->fork[pass], c->traceDone[pass]));
     return HDT_OK;
 }
 

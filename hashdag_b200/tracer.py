@@ -26,12 +26,13 @@ LIB_PATH = os.environ.get("HDT_LIB", os.path.join(_HERE, "libhashdag_b200.so")) 
 DAG_BASIC, DAG_HASH = 0, 1
 COLORS_UNCOMPRESSED, COLORS_COMPRESSED, COLORS_ERRORS, COLORS_HASH = 0, 1, 2, 3
 UNIQUE_OFFSET = 0xFFFFFFFFFFFFFFFF
+OPT_BEAMS, OPT_BEAM_MAX_VISITS, OPT_BEAM_PREFETCH, OPT_BEAM_SERIAL = 1, 2, 3, 4
 
 # EDebugColors, tracer.h:7-17
 DEBUG_NONE, DEBUG_INDEX, DEBUG_POSITION, DEBUG_COLOR_TREE, DEBUG_COLOR_BITS, DEBUG_MIN_COLOR, DEBUG_MAX_COLOR, DEBUG_WEIGHT = range(8)
 
 EXPORTS = (
-    "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_resolve_paths", "hdt_resolve_colors",
+    "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_set_option", "hdt_beam_stats", "hdt_pass_timeline", "hdt_resolve_paths", "hdt_resolve_colors",
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
     "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_launch_count", "hdt_version",
@@ -64,6 +65,9 @@ def load_library():
     lib.hdt_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
     lib.hdt_destroy.argtypes = [C.c_void_p]
     lib.hdt_set_partition.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.hdt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.hdt_beam_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.hdt_pass_timeline.argtypes = [C.c_void_p, C.c_int, fp]
     lib.hdt_resolve_paths.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, d3, d3, d3, d3, fp]
     lib.hdt_resolve_colors.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32,
                                        C.POINTER(ToolInfo), C.c_int, fp]
@@ -365,6 +369,21 @@ class DAGTracer:
     def set_stream(self, cuda_stream_handle):
         """Enqueue on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
         _check(self._lib.hdt_set_stream(self._ctx, cuda_stream_handle))
+
+    def set_option(self, option: int, value: int):
+        """Tuning switches that never change results (OPT_BEAMS: per-tile beam pre-pass on/off)."""
+        _check(self._lib.hdt_set_option(self._ctx, option, value))
+
+    def beam_stats(self) -> dict:
+        out = (C.c_uint64 * 5)()
+        _check(self._lib.hdt_beam_stats(self._ctx, out))
+        return {"root": int(out[0]), "resume": int(out[1]), "hit": int(out[2]), "miss": int(out[3]), "level_sum": int(out[4])}
+
+    def pass_timeline(self, which: int):
+        """(setup end, beam kernel end, per-ray kernel end) of the last paths (0) / shadows (1) pass, ms from its enqueue."""
+        out = (C.c_float * 3)()
+        _check(self._lib.hdt_pass_timeline(self._ctx, which, out))
+        return tuple(out)
 
     def launch_count(self) -> int:
         return int(self._lib.hdt_launch_count(self._ctx))

@@ -89,6 +89,29 @@ const char* hdt_last_error(void);
  * pixel tiles, tile t belongs to rank t % world.  Default: rank 0 of 1 (whole frame). */
 int hdt_set_partition(hdt_ctx* ctx, uint32_t rank, uint32_t world, uint32_t tile_log2);
 
+/* Tuning switches (results never depend on them).  HDT_OPT_BEAMS (default 1): run the per-tile beam
+ * pre-pass of trace_paths / trace_shadows (csrc/hdt_beam.cuh) before the per-ray kernels; 0 makes
+ * every ray start at the root like the reference.  The environment variable HDT_BEAMS=0|1 sets the
+ * default of new contexts. */
+enum {
+    HDT_OPT_BEAMS = 1,
+    HDT_OPT_BEAM_MAX_VISITS = 2, /* nodes a beam may visit before handing over (default 32; env HDT_BEAM_MAX_VISITS) */
+    HDT_OPT_BEAM_PREFETCH = 3,   /* default 0.  1: the ray setup + beam kernels of a paths pass wait only for the previous paths
+                                    kernel instead of for everything queued on the tracer's stream, so that with several frames
+                                    in flight (hdt_resolve_frame_async) they run beside the previous frame's colours / shadows.
+                                    Only valid while nothing queued on the tracer's stream modifies the DAG (static scene, or
+                                    edits applied after hdt_sync()).  env HDT_BEAM_PREFETCH */
+    HDT_OPT_BEAM_SERIAL = 4      /* diagnostics, default 0.  1: the per-ray kernels wait for the beam kernel instead of racing it */
+};
+int hdt_set_option(hdt_ctx* ctx, int option, int value);
+/* Diagnostics of the last beam pre-pass: out[0..3] = tiles that start at the root / resume below it /
+ * were resolved as a common hit / as a common miss; out[4] = sum of the hand-over levels of resuming tiles. */
+int hdt_beam_stats(hdt_ctx* ctx, uint64_t out[5]);
+/* Device timeline of the last paths (pass 0) or shadows (pass 1) pass, in ms from the moment the pass was
+ * enqueued: ms[0] = ray setup finished, ms[1] = beam kernel finished, ms[2] = per-ray kernel finished.
+ * Synchronises both streams of the context. */
+int hdt_pass_timeline(hdt_ctx* ctx, int pass, float ms[3]);
+
 /* ---- the path ------------------------------------------------------------------------------ */
 /* DAGTracer::resolve_paths<TDAG> (dag_tracer.cu:116-143) -> Tracer::trace_paths (tracer.cu:145-252).
  * cam/ray_min/ray_ddx/ray_ddy are TracePathsParams (tracer.h:81-91), i.e. get_trace_params' output. */

@@ -212,3 +212,60 @@ GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
 def test_cuda_against_reference_golden_frames(path):
     from golden_util import check_golden
     check_golden(path, impl="cuda")
+
+
+def _special_cameras(s, fp):
+    """Poses that stress the beam pre-pass: outside the volume (root misses and partial root hits),
+    axis-parallel views (non-tame rays: no beam), direction sign changes inside a tile, grazing views."""
+    c = float(1 << (s.levels - 1))
+    size = float(1 << s.levels)
+    h0 = float(s.heights.get((int(c), int(c)), c))
+    r = float(1 << fp)
+    return [
+        camera.look_at((-0.3 * size, 1.2 * size, -0.2 * size), (c, h0, c)),                  # far outside, volume in view
+        camera.look_at((c - 2.0 * r, h0 + 0.1 * r, c), (c + r, h0 + 0.1 * r, c + 1e-3)),     # grazing, nearly axis-parallel
+        camera.CameraView((c, h0 + 0.6 * r, c), ((1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))),  # straight down
+        camera.CameraView((c + 0.25, h0 + 30.5, c + 0.75), ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))),  # along +z, signs flip mid-frame
+        camera.look_at((c + 7.3, h0 + 3.1, c - 5.2), (c + 40.0, h0 - 6.0, c + 33.0)),         # a few voxels above the ground
+    ]
+
+
+@pytest.mark.parametrize("levels,fp,w,h", [(13, 10, 320, 200), (17, 11, 333, 203), (16, 11, 640, 360)])
+@pytest.mark.parametrize("kind", ["basic", "hash"])
+def test_beam_prepass_never_changes_a_pixel(levels, fp, w, h, kind):
+    """hdt_beam.cuh: frames with the per-tile beam pre-pass == frames without == oracle, and the
+    pre-pass is really exercised (tiles resume below the root)."""
+    from hashdag_b200 import tracer
+    s = get_scene(levels, fp)
+    hashed = kind == "hash"
+    if hashed and not s.has_hash_colors:
+        pytest.skip("no hash colours at this depth")
+    t = tracer.DAGTracer(True, w, h, levels)
+    dag = (tracer.HashDAG if hashed else tracer.BasicDAG).from_scene(s)
+    col = (tracer.HashDAGColors if hashed else tracer.BasicDAGCompressedColors).from_scene(s)
+    odag = hdo.make_dag(s, hdo.DAG_HASH if hashed else hdo.DAG_BASIC)
+    ocol = hdo.make_colors(s, hdo.COLORS_HASH if hashed else hdo.COLORS_COMPRESSED)
+    resumed = 0
+    for cam in scene_cameras(s, 2, fp) + _special_cameras(s, fp):
+        frames = {}
+        for beams in (1, 0):
+            t.set_option(tracer.OPT_BEAMS, beams)
+            t.resolve_paths(cam, _info(s), dag)
+            if beams:
+                st = t.beam_stats()
+                assert st["root"] + st["resume"] + st["hit"] + st["miss"] >= ((w + 7) // 8) * ((h + 3) // 4)
+                resumed += st["resume"] + st["hit"] + st["miss"]
+            p = t.read_paths()
+            t.resolve_colors(dag, col)
+            t.resolve_shadows(cam, _info(s), dag, 1.0, 0.0)
+            frames[beams] = (p, t.read_colors())
+        assert np.array_equal(frames[1][0], frames[0][0]), f"{(frames[1][0] != frames[0][0]).any(-1).sum()} path pixels change with beams"
+        assert np.array_equal(frames[1][1], frames[0][1]), f"{(frames[1][1] != frames[0][1]).sum()} shaded pixels change with beams"
+        prm = camera.trace_params(cam, _info(s), levels, w, h)
+        op, _ = hdo.trace_paths(odag, w, h, prm)
+        assert np.array_equal(frames[1][0], op)
+        oc, _ = hdo.trace_colors(odag, ocol, op)
+        osh, _ = hdo.trace_shadows(odag, prm, op, oc, 1.0, 0.0)
+        assert np.array_equal(frames[1][1], osh)
+    assert resumed > 0, "the beam pre-pass never took over a tile"
+    t.close()
