@@ -1,5 +1,6 @@
-// scratch analysis: visit histograms of the reference DFS (not shipped)
-#include "../oracle/hdo_oracle.cpp"
+// ANALYSIS TOOL (test infrastructure, not shipped): node visits of the reference DFS per level, per ray and
+// per tile, on top of the CPU oracle.  Build + run: python tests/analysis/visit_histogram.py [footprint_log2]
+#include "../../oracle/hdo_oracle.cpp"
 extern "C" int ana_paths(const hdo_dag* dag, uint32_t W, uint32_t H, const double cam[3], const double rmin[3], const double ddx[3],
                     const double ddy[3], uint64_t* visitsByLevel /*32*/, uint64_t* onPathByLevel, uint64_t* raysBySteps /*1024*/, uint64_t* childCount /*9*/, uint64_t* vmCount)
 {

@@ -1,12 +1,17 @@
-import sys, ctypes as C, numpy as np, time
-sys.path.insert(0, '.')
+"""Visits of the reference DFS per level (how much of a frame is top-of-tree work every ray of a tile shares)."""
+import os, subprocess, sys, ctypes as C, numpy as np, time
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+subprocess.run(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                os.path.join(HERE, "visit_histogram.cpp"), "-o", os.path.join(ROOT, "build", "libvisit_histogram.so")], check=True)
 from hashdag_b200 import workloads, camera
 from oracle import hdo
 t=time.time()
 fp = int(sys.argv[1]) if len(sys.argv)>1 else 13
 scene, poses = workloads.build_workload(17, fp, 64)
 print("build", time.time()-t, scene.n_voxels, scene.nodes_per_level)
-lib = C.CDLL('scratch/libana.so')
+lib = C.CDLL(os.path.join(ROOT, 'build', 'libvisit_histogram.so'))
 dag = hdo.make_dag(scene, hdo.DAG_HASH)
 W,H = 1920//2,1080//2
 info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)

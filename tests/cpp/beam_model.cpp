@@ -1,5 +1,12 @@
-// scratch prototype: interval beam pre-pass, CPU. Checks exactness against per-ray DFS and measures savings.
-#include "../oracle/hdo_oracle.cpp"
+// TEST INFRASTRUCTURE: a host model of the beam pre-pass of hashdag_b200/csrc/hdt_beam.cuh, built on the CPU
+// oracle (the only place its internals are reused: this file is compiled by tests/test_beam_model_cpu.py).
+//
+// For every 8x4 (or TWxTH) tile it encloses the tile's rays in intervals, walks the reference DFS with the
+// interval form of compute_intersection_mask (tracer.cu:19-136) until the rays may disagree, then lets each
+// ray resume from that state -- and checks pixel by pixel that resuming gives what the plain per-ray DFS of
+// the oracle gives.  It also counts node visits with and without the pre-pass (the numbers in DESIGN.md §6).
+// The arithmetic argument (monotone correctly-rounded operations => exact enclosures) is in hdt_beam.cuh.
+#include "../../oracle/hdo_oracle.cpp"
 #include <cassert>
 #include <cstdio>
 #include <algorithm>
