@@ -129,7 +129,8 @@ __device__ __forceinline__ float tool_strength(const hdt_tool_info& t, u32 x, u3
 {
     auto sphere = [&](const u32* p, float radius) {
         const float dx = __uint2float_rn(p[0]) - __uint2float_rn(x), dy = __uint2float_rn(p[1]) - __uint2float_rn(y), dz = __uint2float_rn(p[2]) - __uint2float_rn(z);
-        return 1.f - __fdiv_rn(__fsqrt_rn(dx * dx + dy * dy + dz * dz), radius);
+        // length(): the reference's compiled dot is fma(z,z, fma(x,x, y*y)) (its PTX, TOOL_OVERLAY build)
+        return 1.f - __fdiv_rn(__fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)))), radius);
     };
     auto cube = [&](const u32* p, float radius) {
         const float dx = fabsf(__uint2float_rn(p[0]) - __uint2float_rn(x)), dy = fabsf(__uint2float_rn(p[1]) - __uint2float_rn(y)), dz = fabsf(__uint2float_rn(p[2]) - __uint2float_rn(z));

@@ -1,0 +1,218 @@
+"""Edit-dirtied spans of a HashDAG: find them, ship them, apply them to device replicas.
+
+The reference re-uploads after every edit what `HashTable::upload_to_gpu`
+(/root/reference/src/dags/hash_dag/hash_table.cpp:120-184) finds dirty: the whole page table (16 MiB at
+depth 17) and, per bucket that grew, the new words -- one cudaMemcpyAsync each -- plus the colour tree
+and every rebuilt colour leaf (hash_dag_colors.h:102-120).  Here one edit becomes one packed delta
+(`{dst_word, src_word, n_words}` spans + payload) that is broadcast once to every GPU
+(torch.distributed) and applied by one kernel launch per array (`hdt_apply_ranges`), on the tracer's
+stream, in order with the frames around it.  Edits themselves (find_or_add into the hash table) stay with
+the host editor; this module only needs the arrays before and after.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+RANGE_DTYPE = np.dtype([("dst_word", "<u8"), ("src_word", "<u8"), ("n_words", "<u8")])   # hdt_range
+
+
+def dirty_spans(old: np.ndarray, new: np.ndarray, n_new: int | None = None, merge_gap: int = 32):
+    """Spans of `new[:n_new]` that differ from `old` (everything beyond len(old) counts as changed).
+    -> (ranges[RANGE_DTYPE], payload) with payload = the spans' words back to back.
+    Spans closer than `merge_gap` words are merged: fewer, longer copies."""
+    old = np.ascontiguousarray(old).reshape(-1)
+    new = np.ascontiguousarray(new).reshape(-1)
+    assert old.dtype == new.dtype
+    n_new = new.size if n_new is None else int(n_new)
+    common = min(old.size, n_new)
+    idx = np.flatnonzero(old[:common] != new[:common])
+    starts, ends = [], []
+    if idx.size:
+        cut = np.flatnonzero(np.diff(idx) > merge_gap)
+        starts = idx[np.concatenate(([0], cut + 1))].tolist()
+        ends = (idx[np.concatenate((cut, [idx.size - 1]))] + 1).tolist()
+    if n_new > common:
+        if ends and common - ends[-1] <= merge_gap:
+            ends[-1] = n_new
+        else:
+            starts.append(common)
+            ends.append(n_new)
+    ranges = np.zeros(len(starts), dtype=RANGE_DTYPE)
+    chunks, src = [], 0
+    for i, (a, b) in enumerate(zip(starts, ends)):
+        ranges[i] = (a, src, b - a)
+        chunks.append(new[a:b])
+        src += b - a
+    payload = np.concatenate(chunks) if chunks else np.zeros(0, dtype=new.dtype)
+    return ranges, payload
+
+
+def apply_spans_host(dst: np.ndarray, ranges: np.ndarray, payload: np.ndarray) -> None:
+    """Host mirror of apply_ranges_kernel (csrc/hdt_tracer.cu): dst[r.dst_word + i] = payload[r.src_word + i]."""
+    for r in ranges:
+        d, s, n = int(r["dst_word"]), int(r["src_word"]), int(r["n_words"])
+        dst[d:d + n] = payload[s:s + n]
+
+
+@dataclass
+class ColorLeafArrays:
+    """One unique colour leaf (CompressedColorLeaf, vwsc.h:157-191) as host arrays."""
+    weights: np.ndarray
+    blocks: np.ndarray
+    macro_blocks: np.ndarray
+
+    def same_as(self, o) -> bool:
+        return o is not None and np.array_equal(self.weights, o.weights) and np.array_equal(self.blocks, o.blocks) and np.array_equal(self.macro_blocks, o.macro_blocks)
+
+
+@dataclass
+class DagDelta:
+    """Everything a replica needs to follow one edit."""
+    first_node_index: int
+    pool_top: int
+    pool_ranges: np.ndarray
+    pool_payload: np.ndarray            # uint32
+    table_ranges: np.ndarray
+    table_payload: np.ndarray           # uint32
+    color_node_ranges: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=RANGE_DTYPE))
+    color_node_payload: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.uint32))
+    n_color_nodes: int = 0
+    color_leaves: dict = field(default_factory=dict)   # leaf index -> ColorLeafArrays (new or rebuilt leaves)
+    n_color_leaves: int = 0
+
+    @property
+    def nbytes(self) -> int:
+        n = sum(a.nbytes for a in (self.pool_ranges, self.pool_payload, self.table_ranges, self.table_payload, self.color_node_ranges, self.color_node_payload))
+        return n + sum(l.weights.nbytes + l.blocks.nbytes + l.macro_blocks.nbytes for l in self.color_leaves.values())
+
+
+def diff_hash_dag(old_pool, old_table, new_pool, new_table, first_node_index, pool_top,
+                  old_color_nodes=None, new_color_nodes=None, old_leaves=None, new_leaves=None) -> DagDelta:
+    """Delta between two versions of a HashDAG (+ its HashDAGColors tree and unique leaves)."""
+    pr, pp = dirty_spans(old_pool, new_pool, int(pool_top) * 512)
+    tr, tp = dirty_spans(old_table, new_table)
+    d = DagDelta(int(first_node_index), int(pool_top), pr, pp, tr, tp)
+    if new_color_nodes is not None:
+        d.color_node_ranges, d.color_node_payload = dirty_spans(old_color_nodes if old_color_nodes is not None else np.zeros(0, np.uint32), new_color_nodes)
+        d.n_color_nodes = int(new_color_nodes.size)
+    if new_leaves is not None:
+        old_leaves = old_leaves or []
+        d.n_color_leaves = len(new_leaves)
+        for i, leaf in enumerate(new_leaves):
+            if not leaf.same_as(old_leaves[i] if i < len(old_leaves) else None):
+                d.color_leaves[i] = leaf
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+# shipping a delta to the other ranks
+# ---------------------------------------------------------------------------------------------
+def broadcast_delta(delta: DagDelta | None, src: int = 0, device="cpu") -> DagDelta:
+    """Rank `src` passes its delta, the others None; everybody returns the delta.  One object broadcast for
+    the sizes, one tensor broadcast for all the payload bytes (device="cuda:N" with the nccl backend)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    names = ("pool_ranges", "pool_payload", "table_ranges", "table_payload", "color_node_ranges", "color_node_payload")
+    if rank == src:
+        arrays = [np.ascontiguousarray(getattr(delta, n)) for n in names]
+        leaf_ids = sorted(delta.color_leaves)
+        for i in leaf_ids:
+            l = delta.color_leaves[i]
+            arrays += [np.ascontiguousarray(l.weights), np.ascontiguousarray(l.blocks), np.ascontiguousarray(l.macro_blocks)]
+        head = {"first": delta.first_node_index, "top": delta.pool_top, "n_color_nodes": delta.n_color_nodes, "n_color_leaves": delta.n_color_leaves,
+                "leaf_ids": leaf_ids, "sizes": [(a.dtype.str if a.dtype.names is None else "range", int(a.size)) for a in arrays]}
+        box = [head]
+    else:
+        box = [None]
+    dist.broadcast_object_list(box, src=src)
+    head = box[0]
+    nbytes = [n * (RANGE_DTYPE.itemsize if dt == "range" else np.dtype(dt).itemsize) for dt, n in head["sizes"]]
+    offs = np.concatenate(([0], np.cumsum([(b + 7) // 8 * 8 for b in nbytes]))).astype(np.int64)
+    total = int(offs[-1])
+    if rank == src:
+        flat = np.zeros(total, dtype=np.uint8)
+        for a, o, b in zip(arrays, offs, nbytes):
+            flat[o:o + b] = a.view(np.uint8).reshape(-1)
+        t = torch.from_numpy(flat).to(device)
+    else:
+        t = torch.empty(total, dtype=torch.uint8, device=device)
+    if total:
+        dist.broadcast(t, src=src)
+    if rank == src:
+        return delta
+    flat = t.cpu().numpy()
+    out = []
+    for (dt, n), o, b in zip(head["sizes"], offs, nbytes):
+        out.append(flat[o:o + b].view(RANGE_DTYPE if dt == "range" else np.dtype(dt)).copy())
+    d = DagDelta(head["first"], head["top"], out[0], out[1], out[2], out[3], out[4], out[5], head["n_color_nodes"], {}, head["n_color_leaves"])
+    for k, i in enumerate(head["leaf_ids"]):
+        d.color_leaves[i] = ColorLeafArrays(out[6 + 3 * k], out[7 + 3 * k], out[8 + 3 * k])
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+# device replicas
+# ---------------------------------------------------------------------------------------------
+class HashDagReplica:
+    """One GPU's copy of a HashDAG (+ colours) that follows edits through deltas.  Needs CUDA."""
+
+    def __init__(self, tracer_obj, pool, page_table, pool_top, first_node_index, levels, pool_capacity_pages,
+                 color_nodes=None, color_offsets=None, main_leaf=None, color_node_capacity=0, device="cuda:0"):
+        import torch
+        from . import tracer as T
+        self._T, self._torch, self.tracer, self.device, self.levels = T, torch, tracer_obj, device, levels
+        cap = max(int(pool_capacity_pages), int(pool_top)) * 512
+        self.pool = torch.zeros(cap, dtype=torch.int32, device=device)
+        self.pool[: pool.size] = T._to_device(pool, device)
+        self.page_table = T._to_device(page_table, device)
+        self.pool_top, self.first_node_index = int(pool_top), int(first_node_index)
+        self.has_colors = color_nodes is not None
+        if self.has_colors:
+            ncap = max(int(color_node_capacity), int(color_nodes.size))
+            self.color_nodes = torch.zeros(ncap, dtype=torch.int32, device=device)
+            self.color_nodes[: color_nodes.size] = T._to_device(color_nodes, device)
+            self.n_color_nodes = int(color_nodes.size)
+            self.color_offsets = T._to_device(color_offsets, device)
+            self.main_leaf = main_leaf                  # tracer.CompressedColorLeaf on this device
+            self.leaves = {}                            # index -> tracer.CompressedColorLeaf (keeps the tensors alive)
+            self.leaf_pods = None                       # int64 tensor, 13 words per leaf (CompressedColorLeaf, 104 B)
+
+    def apply(self, delta: DagDelta) -> None:
+        T, torch = self._T, self._torch
+        if int(delta.pool_top) * 512 > self.pool.numel():
+            raise T.TracerError("HashDagReplica: the edit outgrew the replica's pool capacity")
+
+        def spans(dst, ranges, payload):
+            if len(ranges):
+                self.tracer.apply_ranges(dst, T._to_device(payload, self.device), torch.from_numpy(ranges.view(np.int64).reshape(-1, 3).copy()).to(self.device), len(ranges))
+        spans(self.pool, delta.pool_ranges, delta.pool_payload)
+        spans(self.page_table, delta.table_ranges, delta.table_payload)
+        self.pool_top, self.first_node_index = int(delta.pool_top), int(delta.first_node_index)
+        if self.has_colors and delta.n_color_nodes:
+            if delta.n_color_nodes > self.color_nodes.numel():
+                grown = torch.zeros(2 * delta.n_color_nodes, dtype=torch.int32, device=self.device)
+                grown[: self.color_nodes.numel()] = self.color_nodes
+                self.tracer.sync()
+                self.color_nodes = grown
+            spans(self.color_nodes, delta.color_node_ranges, delta.color_node_payload)
+            self.n_color_nodes = delta.n_color_nodes
+            for i, l in delta.color_leaves.items():
+                self.leaves[i] = T.CompressedColorLeaf(T._to_device(l.weights, self.device), T._to_device(l.blocks, self.device),
+                                                       T._to_device(l.macro_blocks, self.device), T.UNIQUE_OFFSET)
+            if delta.n_color_leaves:
+                pods = np.zeros((delta.n_color_leaves, 13), dtype=np.uint64)
+                for i in range(delta.n_color_leaves):
+                    if i in self.leaves:
+                        pods[i] = np.frombuffer(self.leaves[i].pod(), dtype=np.uint64)
+                self.tracer.sync()                      # frames in flight may still read the previous POD array
+                self.leaf_pods = T._to_device(pods.reshape(-1), self.device)
+
+    def dag(self):
+        return self._T.HashDAG(self.pool, self.page_table, self.pool_top, self.first_node_index, self.levels)
+
+    def colors(self):
+        T = self._T
+        return T.HashDAGColors(self.color_nodes[: self.n_color_nodes], self.color_offsets, self.main_leaf, self.leaf_pods)

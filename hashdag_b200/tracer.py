@@ -366,6 +366,10 @@ class DAGTracer:
     def assemble_colors(self, gathered_tensor, frame_tensor=None):
         _check(self._lib.hdt_assemble_colors(self._ctx, gathered_tensor.data_ptr(), 0 if frame_tensor is None else frame_tensor.data_ptr()))
 
+    def apply_ranges(self, dst_tensor, payload_tensor, ranges_tensor, n_ranges: int):
+        """dst[r.dst_word + i] = payload[r.src_word + i] for every hdt_range r (edit-dirtied spans, see edits.py)."""
+        _check(self._lib.hdt_apply_ranges(self._ctx, dst_tensor.data_ptr(), payload_tensor.data_ptr(), ranges_tensor.data_ptr(), n_ranges))
+
     def set_stream(self, cuda_stream_handle):
         """Enqueue on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
         _check(self._lib.hdt_set_stream(self._ctx, cuda_stream_handle))

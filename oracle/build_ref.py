@@ -22,6 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src"
 OUT_DIR = os.path.join(HERE, "_ref")
 HARNESS = os.path.join(HERE, "ref_harness", "ref_harness.cu")
+HARNESS_FILES = [HARNESS, os.path.join(HERE, "ref_harness", "ref_harness_edits.cpp"), os.path.join(HERE, "ref_harness", "ref_harness_shared.h")]
 
 # (depth, width, height): golden/parity variants are small, the bench variant is the headline config
 VARIANTS = [
@@ -56,18 +57,19 @@ inline void glDeleteTextures(GLsizei, const GLuint*) {}
 """
 
 
-def lib_path(depth, width, height):
-    return os.path.join(OUT_DIR, f"libhashdag_ref_d{depth}_{width}x{height}.so")
+def lib_path(depth, width, height, overlay=False):
+    return os.path.join(OUT_DIR, f"libhashdag_ref_d{depth}_{width}x{height}{'_overlay' if overlay else ''}.so")
 
 
-def build_variant(depth, width, height, force=False, verbose=True):
+def build_variant(depth, width, height, force=False, verbose=True, overlay=False):
+    """overlay=True: the same build with TOOL_OVERLAY 1 (off under BENCHMARK, typedefs.h:70-72), to pin the tool overlay."""
     if not os.path.isdir(REF_SRC):
         return None  # GPU box: prebuilt libraries only
-    out = lib_path(depth, width, height)
-    if os.path.exists(out) and not force and os.path.getmtime(out) >= max(os.path.getmtime(HARNESS), os.path.getmtime(__file__)):
+    out = lib_path(depth, width, height, overlay)
+    if os.path.exists(out) and not force and os.path.getmtime(out) >= max([os.path.getmtime(f) for f in HARNESS_FILES] + [os.path.getmtime(__file__)]):
         return out
     os.makedirs(OUT_DIR, exist_ok=True)
-    stage = f"/tmp/hashdag_ref_stage_d{depth}_{width}x{height}"
+    stage = f"/tmp/hashdag_ref_stage_d{depth}_{width}x{height}{'_overlay' if overlay else ''}"
     shutil.rmtree(stage, ignore_errors=True)
     shutil.copytree(REF_SRC, os.path.join(stage, "src"))
     os.makedirs(os.path.join(stage, "stub", "GL"))
@@ -77,7 +79,7 @@ def build_variant(depth, width, height, force=False, verbose=True):
     with open(os.path.join(stage, "src", "script_definitions.h"), "w") as f:
         f.write(f"#define SCENE_DEPTH {depth}\n#define REPLAY_DEPTH {depth}\n#define BENCHMARK 1\n#define HEADLESS 1\n#define ENABLE_CHECKS 0\n"
                 # the library is dlopen()ed into python: keep the reference from replacing global new/delete
-                "#define TRACK_GLOBAL_NEWDELETE 0\n")
+                "#define TRACK_GLOBAL_NEWDELETE 0\n" + ("#define TOOL_OVERLAY 1\n" if overlay else ""))
     tpath = os.path.join(stage, "src", "typedefs.h")
     text = open(tpath, encoding="utf-8-sig").read()
     text, n1 = re.subn(r"constexpr uint32 imageWidth = \d+;", f"constexpr uint32 imageWidth = {width};", text)
@@ -86,10 +88,10 @@ def build_variant(depth, width, height, force=False, verbose=True):
     open(tpath, "w").write(text)
     # .cu files (and the harness) are CUDA; the reference's .cpp files are host C++ that only
     # needs the CUDA headers -- the same split its CMakeLists.txt makes.
-    src = [os.path.join(stage, "src", f) for f in REF_FILES] + [HARNESS]
+    src = [os.path.join(stage, "src", f) for f in REF_FILES] + HARNESS_FILES[:2]
     common = ["nvcc", "-std=c++17", "--expt-relaxed-constexpr", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-w", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique",  # several variants share one process
-              "-I" + os.path.join(stage, "stub"), "-I" + os.path.join(stage, "src")]
+              "-I" + os.path.join(stage, "stub"), "-I" + os.path.join(stage, "src"), "-I" + os.path.join(HERE, "ref_harness")]
     if verbose:
         print(f"[build_ref] d{depth} {width}x{height} -> {os.path.relpath(out, HERE)}", flush=True)
     procs, objs = [], []
@@ -106,12 +108,13 @@ def build_variant(depth, width, height, force=False, verbose=True):
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-4000:] + r.stderr[-8000:])
         raise RuntimeError(f"reference link failed for d{depth} {width}x{height}")
-    shutil.rmtree(stage, ignore_errors=True)
+    if not os.environ.get("HDT_KEEP_STAGE"):
+        shutil.rmtree(stage, ignore_errors=True)
     return out
 
 
 def build_all(force=False):
-    return [build_variant(*v, force=force) for v in VARIANTS]
+    return [build_variant(*v, force=force) for v in VARIANTS] + [build_variant(13, 256, 256, force=force, overlay=True)]
 
 
 if __name__ == "__main__":

@@ -337,7 +337,8 @@ inline float tool_strength(const hdo_tool_info& t, u32 x, u32 y, u32 z)  // trac
 {
     auto sphere = [&](const u32* p, float radius) {
         const float dx = float(p[0]) - float(x), dy = float(p[1]) - float(y), dz = float(p[2]) - float(z);
-        return 1 - std::sqrt(dx * dx + dy * dy + dz * dz) / radius;
+        // length(): dot contracted by nvcc as fma(z,z, fma(x,x, y*y)) (read off the reference's PTX, TOOL_OVERLAY build)
+        return 1 - std::sqrt(fmaf(dz, dz, fmaf(dx, dx, dy * dy))) / radius;
     };
     auto cube = [&](const u32* p, float radius) {
         const float dx = std::fabs(float(p[0]) - float(x)), dy = std::fabs(float(p[1]) - float(y)), dz = std::fabs(float(p[2]) - float(z));

@@ -16,12 +16,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def lib_path(depth, width, height):
-    return os.path.join(_HERE, "_ref", f"libhashdag_ref_d{depth}_{width}x{height}.so")
+def lib_path(depth, width, height, overlay=False):
+    return os.path.join(_HERE, "_ref", f"libhashdag_ref_d{depth}_{width}x{height}{'_overlay' if overlay else ''}.so")
 
 
-def available(depth, width, height):
-    return os.path.exists(lib_path(depth, width, height))
+def available(depth, width, height, overlay=False):
+    return os.path.exists(lib_path(depth, width, height, overlay))
 
 
 def _d(v):
@@ -30,8 +30,8 @@ def _d(v):
 
 
 class RefTracer:
-    def __init__(self, depth, width, height, device=0):
-        path = lib_path(depth, width, height)
+    def __init__(self, depth, width, height, device=0, overlay=False):
+        path = lib_path(depth, width, height, overlay)
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run `python oracle/build_ref.py` where /root/reference exists")
         self.lib = l = C.CDLL(path)
@@ -55,6 +55,14 @@ class RefTracer:
         l.ref_read_paths.argtypes = [C.c_void_p]
         l.ref_read_colors.argtypes = [C.c_void_p]
         l.ref_write_colors.argtypes = [C.c_void_p]
+        if hasattr(l, "ref_edit_sphere"):
+            u3 = C.POINTER(C.c_uint32)
+            l.ref_edit_sphere.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
+            l.ref_color_leaf_count.restype = C.c_uint64
+            l.ref_color_leaf_info.argtypes = [C.c_uint64] + [C.POINTER(C.c_uint64)] * 3
+            l.ref_color_leaf_copy.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+            l.ref_resolve_colors_tool.restype = C.c_float
+            l.ref_resolve_colors_tool.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, u3, C.c_float, u3, u3]
         if l.ref_init(device) != 0:
             raise RuntimeError("ref_init failed (no CUDA device?)")
         self.scene = None
@@ -98,6 +106,28 @@ class RefTracer:
         offs = np.empty(b.value, dtype=np.uint64)
         self.lib.ref_hash_colors_copy(nodes.ctypes.data, offs.ctypes.data)
         return nodes, offs
+
+    def edit_sphere(self, center, radius, adding):
+        """The reference's own CPU edit (SphereEditor<adding>, hash_dag_editors.h:273-313) + upload_to_gpu."""
+        assert self.lib.ref_edit_sphere(float(center[0]), float(center[1]), float(center[2]), float(radius), int(bool(adding))) == 0
+
+    def color_leaves(self):
+        """Unique colour leaves created by edits: list of (weights, blocks, macro_blocks)."""
+        out = []
+        for i in range(int(self.lib.ref_color_leaf_count())):
+            a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            assert self.lib.ref_color_leaf_info(i, C.byref(a), C.byref(b), C.byref(c)) == 0
+            w, bl, m = np.zeros(a.value, np.uint32), np.zeros(b.value, np.uint64), np.zeros(c.value, np.uint64)
+            assert self.lib.ref_color_leaf_copy(i, w.ctypes.data, bl.ctypes.data, m.ctypes.data) == 0
+            out.append((w, bl, m))
+        return out
+
+    def tool_overlay_compiled(self):
+        return bool(self.lib.ref_tool_overlay_compiled())
+
+    def resolve_colors_tool(self, dag_kind, colors_kind, tool_kind, position, radius, copy_source=(0, 0, 0), copy_dest=(0, 0, 0), debug_colors=0, debug_level=0):
+        u3 = lambda v: (C.c_uint32 * 3)(*[int(x) for x in v])
+        return self.lib.ref_resolve_colors_tool(dag_kind, colors_kind, debug_colors, debug_level, int(tool_kind), u3(position), float(radius), u3(copy_source), u3(copy_dest))
 
     def resolve_paths(self, dag_kind, camera, info):
         return self.lib.ref_resolve_paths(dag_kind, _d(camera.position), _d(camera.rotation), _d(info.bounds_min), _d(info.bounds_max))

@@ -5,46 +5,21 @@
 //
 // Depth and resolution are compile-time in the reference (typedefs.h:517,683-684), hence one
 // library per (depth, width, height).
-#include <cstdint>
-#include <cstdio>
-#include <cstring>
-#include <memory>
-#include <string>
-#include <vector>
-#include <mutex>
-#include <atomic>
-#include <unordered_map>
-#include <array>
-#include <random>
-#include <set>
-#include <limits>
-#include <chrono>
-#include <type_traits>
-#include <cmath>
+#include "ref_harness_shared.h"
 
-// The frame surfaces, the HashTable pointers and the colour arrays are private in the reference
-// and it has no full-frame read-back; this translation unit alone looks inside.
-#define private public
-#define protected public
-#include "dag_tracer.h"
-#include "dags/basic_dag/basic_dag.h"
-#include "dags/hash_dag/hash_dag.h"
-#include "dags/hash_dag/hash_dag_colors.h"
-#include "dags/hash_dag/hash_dag_factory.h"
-#include "memory.h"
-#undef private
-#undef protected
+namespace refh {
+HashDAG g_hash;
+HashDAGColors g_hashColors;
+bool g_hasHash = false, g_hasHashColors = false;
+}
+using namespace refh;
 
 namespace {
 std::unique_ptr<DAGTracer> g_tracer;
 BasicDAG g_basic;
-HashDAG g_hash;
 BasicDAGCompressedColors g_compressed;
 BasicDAGUncompressedColors g_uncompressed;
 BasicDAGColorErrors g_errors;
-HashDAGColors g_hashColors;
-HashDAGUndoRedo* g_unused = nullptr;
-bool g_hasHash = false, g_hasHashColors = false;
 
 CameraView make_camera(const double pos[3], const double rot[9])
 {
@@ -189,6 +164,20 @@ float ref_resolve_colors(int dagKind, int colorsKind, int debugColors, uint32_t 
     g_errors.compressedColors = g_compressed;
     g_errors.uncompressedColors = g_uncompressed;
     return g_tracer->resolve_colors(g_basic, g_errors, dbg, debugLevel, tool);
+}
+
+// Tracer::trace_colors with a tool overlay (tracer.cu:276-286; compiled in only when TOOL_OVERLAY is set,
+// i.e. in the "_overlay" variant of this library).  toolKind: ETool as int, then ToolInfo's fields.
+int ref_tool_overlay_compiled() { return TOOL_OVERLAY ? 1 : 0; }
+float ref_resolve_colors_tool(int dagKind, int colorsKind, int debugColors, uint32_t debugLevel, int toolKind, const uint32_t position[3], float radius,
+                              const uint32_t copySource[3], const uint32_t copyDest[3])
+{
+    const ToolInfo tool(ETool(toolKind), make_uint3(position[0], position[1], position[2]), radius,
+                        make_uint3(copySource[0], copySource[1], copySource[2]), make_uint3(copyDest[0], copyDest[1], copyDest[2]));
+    const EDebugColors dbg = EDebugColors(debugColors);
+    if (dagKind == 1) return g_tracer->resolve_colors(g_hash, g_hashColors, dbg, debugLevel, tool);
+    if (colorsKind == 0) return g_tracer->resolve_colors(g_basic, g_uncompressed, dbg, debugLevel, tool);
+    return g_tracer->resolve_colors(g_basic, g_compressed, dbg, debugLevel, tool);
 }
 
 float ref_resolve_shadows(int dagKind, const double pos[3], const double rot[9], const double bmin[3], const double bmax[3], float bias, float fog)

@@ -1,0 +1,53 @@
+// The reference's CPU edit code behind the harness (host C++: see ref_harness_shared.h for why it is a separate file).
+// TEST INFRASTRUCTURE: built by oracle/build_ref.py into oracle/_ref/, never linked into the product.
+#include "ref_harness_shared.h"
+#define private public
+#include "dags/hash_dag/hash_dag_editors.h"
+#undef private
+
+using namespace refh;
+
+namespace {
+HashDAGUndoRedo g_undoRedo;
+StatsRecorder g_statsRecorder;
+}
+
+extern "C" {
+
+// The reference's own CPU edit of the HashDAG, as Engine::edit drives it (engine.h:78-103): build the
+// editor, HashDAG::edit_threads (hash_dag.h:255-406), HashTable::upload_to_gpu (hash_table.cpp:120-184).
+int ref_edit_sphere(float x, float y, float z, float radius, int adding)
+{
+    if (!g_hasHash || !g_hasHashColors) return 1;
+    if (adding) {
+        const auto tool = SphereEditor<true>(make_float3(x, y, z), radius);
+        g_hash.edit_threads(tool, g_hashColors, g_undoRedo, g_statsRecorder);
+    } else {
+        const auto tool = SphereEditor<false>(make_float3(x, y, z), radius);
+        g_hash.edit_threads(tool, g_hashColors, g_undoRedo, g_statsRecorder);
+    }
+    g_hash.data.upload_to_gpu();
+    return 0;
+}
+
+// Unique colour leaves created by edits (HashDAGColors::leaves, hash_dag_colors.h:65-73).
+uint64_t ref_color_leaf_count() { return g_hasHashColors ? g_hashColors.leaves_CPU.size() : 0; }
+int ref_color_leaf_info(uint64_t i, uint64_t* nWeights, uint64_t* nBlocks, uint64_t* nMacro)
+{
+    if (!g_hasHashColors || i >= g_hashColors.leaves_CPU.size()) return 1;
+    const CompressedColorLeaf& l = g_hashColors.leaves_CPU[i];
+    *nWeights = l.weights_CPU.size(); *nBlocks = l.blocks_CPU.size(); *nMacro = l.macroBlocks_CPU.size();
+    return 0;
+}
+int ref_color_leaf_copy(uint64_t i, uint32_t* weights, uint64_t* blocks, uint64_t* macro)
+{
+    if (!g_hasHashColors || i >= g_hashColors.leaves_CPU.size()) return 1;
+    const CompressedColorLeaf& l = g_hashColors.leaves_CPU[i];
+    if (l.weights_CPU.size()) std::memcpy(weights, l.weights_CPU.data(), l.weights_CPU.size() * sizeof(uint32));
+    if (l.blocks_CPU.size()) std::memcpy(blocks, l.blocks_CPU.data(), l.blocks_CPU.size() * sizeof(uint64));
+    if (l.macroBlocks_CPU.size()) std::memcpy(macro, l.macroBlocks_CPU.data(), l.macroBlocks_CPU.size() * sizeof(uint64));
+    return 0;
+}
+
+
+}  // extern "C"

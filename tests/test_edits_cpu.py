@@ -1,0 +1,84 @@
+"""CPU: the dirty-span service (hashdag_b200/edits.py) -- span extraction, host mirror of the apply kernel,
+and the world-2 broadcast (gloo) that replicas follow edits through."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import get_scene
+from hashdag_b200 import edits
+
+
+def test_spans_reproduce_the_new_array_and_stay_small():
+    rng = np.random.default_rng(5)
+    old = rng.integers(0, 2**32, 200_000, dtype=np.uint32)
+    for trial in range(20):
+        new = np.concatenate([old, rng.integers(0, 2**32, int(rng.integers(0, 3000)), dtype=np.uint32)]) if trial % 2 else old.copy()
+        for _ in range(int(rng.integers(0, 12))):
+            a = int(rng.integers(0, old.size - 600)); n = int(rng.integers(1, 600))
+            new[a:a + n] = rng.integers(0, 2**32, n, dtype=np.uint32)
+        n_new = new.size - (7 if trial % 4 == 3 else 0)
+        ranges, payload = edits.dirty_spans(old, new, n_new)
+        dst = np.zeros(max(old.size, n_new), np.uint32); dst[: old.size] = old
+        edits.apply_spans_host(dst, ranges, payload)
+        assert np.array_equal(dst[:n_new], new[:n_new])
+        assert payload.size == int(ranges["n_words"].sum()) and payload.size <= (new[: old.size] != old).sum() + (new.size - old.size) + 32 * (len(ranges) + 12)
+        assert np.all(ranges["dst_word"][1:] >= ranges["dst_word"][:-1] + ranges["n_words"][:-1])      # ordered, disjoint
+    r, p = edits.dirty_spans(old, old)
+    assert len(r) == 0 and p.size == 0
+
+
+def _leaf(rng, n):
+    return edits.ColorLeafArrays(rng.integers(0, 2**32, n, dtype=np.uint32), rng.integers(0, 2**63, n, dtype=np.uint64), rng.integers(0, 2**63, 2, dtype=np.uint64))
+
+
+def test_delta_between_two_hash_dags():
+    a, b = get_scene(13, 10), get_scene(13, 10, seed=99)
+    rng = np.random.default_rng(1)
+    la = [_leaf(rng, 5)]
+    lb = [la[0], _leaf(rng, 9)]
+    d = edits.diff_hash_dag(a.hash_pool, a.hash_page_table, b.hash_pool, b.hash_page_table, b.hash_first_node_index, b.hash_pool_top,
+                            a.color_nodes, b.color_nodes, la, lb)
+    pool = np.zeros(max(a.hash_pool.size, b.hash_pool.size), np.uint32); pool[: a.hash_pool.size] = a.hash_pool
+    edits.apply_spans_host(pool, d.pool_ranges, d.pool_payload)
+    table = a.hash_page_table.copy(); edits.apply_spans_host(table, d.table_ranges, d.table_payload)
+    nodes = np.zeros(max(a.color_nodes.size, b.color_nodes.size), np.uint32); nodes[: a.color_nodes.size] = a.color_nodes
+    edits.apply_spans_host(nodes, d.color_node_ranges, d.color_node_payload)
+    assert np.array_equal(pool[: b.hash_pool.size], b.hash_pool) and np.array_equal(table, b.hash_page_table)
+    assert np.array_equal(nodes[: b.color_nodes.size], b.color_nodes)
+    assert sorted(d.color_leaves) == [1] and d.n_color_leaves == 2 and d.first_node_index == b.hash_first_node_index
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = get_scene(13, 10), get_scene(13, 10, seed=99)
+        rng = np.random.default_rng(1)
+        delta = None
+        if rank == 0:   # only rank 0 runs the editor and knows the new version
+            delta = edits.diff_hash_dag(a.hash_pool, a.hash_page_table, b.hash_pool, b.hash_page_table, b.hash_first_node_index, b.hash_pool_top,
+                                        a.color_nodes, b.color_nodes, [], [_leaf(rng, 4), _leaf(rng, 11)])
+        delta = edits.broadcast_delta(delta, src=0)
+        pool = np.zeros(max(a.hash_pool.size, delta.pool_top * 512), np.uint32); pool[: a.hash_pool.size] = a.hash_pool
+        edits.apply_spans_host(pool, delta.pool_ranges, delta.pool_payload)
+        table = a.hash_page_table.copy(); edits.apply_spans_host(table, delta.table_ranges, delta.table_payload)
+        ok = np.array_equal(pool[: b.hash_pool.size], b.hash_pool) and np.array_equal(table, b.hash_page_table)
+        ok = ok and delta.first_node_index == b.hash_first_node_index and sorted(delta.color_leaves) == [0, 1] and delta.color_leaves[1].weights.size == 11
+        np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok), delta.nbytes]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicas_follow_an_edit_through_one_broadcast(tmp_path):
+    get_scene(13, 10); get_scene(13, 10, seed=99)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "ok0.npy"), np.load(tmp_path / "ok1.npy")
+    assert r0[0] == 1 and r1[0] == 1 and r0[1] == r1[1] > 0

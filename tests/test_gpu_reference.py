@@ -1,5 +1,7 @@
 """GPU: the UNMODIFIED reference kernels (oracle/_ref, built by oracle/build_ref.py) against the
 oracle and the product on identical inputs.  This is what pins the oracle."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -108,3 +110,49 @@ def test_config5_depth16_1080p_basic_vs_hash_with_fog():
         assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
         assert frames[0][0][..., :3].any(-1).mean() > 0.3
     t.close()
+
+
+def test_tool_overlay_matches_the_reference_built_with_TOOL_OVERLAY():
+    """ToolInfo::strength + the lerp towards red (tracer.h:51-76, tracer.cu:276-286).  The BENCHMARK build of
+    the reference compiles the overlay out (typedefs.h:70-72); oracle/_ref holds one variant built with
+    TOOL_OVERLAY 1 for this test.  Sphere, cube and copy tools, BasicDAG and HashDAG, product and oracle."""
+    from hashdag_b200 import tracer
+    from oracle import hdo
+    scene = gu.recipe_scene("d13")
+    if not ref.available(13, gu.W, gu.H, overlay=True):
+        pytest.skip("oracle/_ref overlay variant not built")
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    rt = ref.RefTracer(13, gu.W, gu.H, overlay=True)
+    assert rt.tool_overlay_compiled()
+    rt.load_scene(scene)
+    t = tracer.DAGTracer(True, gu.W, gu.H, 13)
+    pose = gu.recipe_poses(scene)[0]
+    c = 1 << 12
+    h0 = scene.heights[(c, c)]
+    tools = [(0, (c + 10, h0 + 2, c + 5), 40.0, (0, 0, 0), (0, 0, 0)), (1, (c - 60, h0, c + 30), 7.5, (0, 0, 0), (0, 0, 0)),
+             (3, (c + 35, h0 + 5, c - 20), 22.0, (0, 0, 0), (0, 0, 0)), (4, (c, h0, c), 30.0, (c + 50, h0 + 3, c + 50), (c - 45, h0 + 1, c - 40)),
+             (5, (c + 5, h0 + 1, c + 5), 300.0, (c, h0, c), (c + 2, h0, c + 2))]
+    hit_overlay = 0
+    for dk, ck, dag, col, okind in ((0, 1, tracer.BasicDAG.from_scene(scene), tracer.BasicDAGCompressedColors.from_scene(scene), hdo.COLORS_COMPRESSED),
+                                    (1, 3, tracer.HashDAG.from_scene(scene), tracer.HashDAGColors.from_scene(scene), hdo.COLORS_HASH)):
+        odag, ocol = hdo.make_dag(scene, dk), hdo.make_colors(scene, okind)
+        rt.resolve_paths(dk, pose, info)
+        t.resolve_paths(pose, info, dag)
+        paths = t.read_paths()
+        assert np.array_equal(paths, rt.read_paths())
+        rt.resolve_colors(dk, ck)
+        plain = rt.read_colors()
+        for kind, pos, radius, src, dst in tools:
+            rt.resolve_colors_tool(dk, ck, kind, pos, radius, src, dst)
+            want = rt.read_colors()
+            ti = tracer.ToolInfo(kind, (C.c_uint32 * 3)(*pos), radius, (C.c_uint32 * 3)(*src), (C.c_uint32 * 3)(*dst))
+            t.resolve_colors(dag, col, 0, 0, ti, True)
+            got = t.read_colors()
+            assert np.array_equal(got, want), f"tool {kind} dag {dk}: {(got != want).sum()} pixels differ from the reference"
+            oti = hdo.ToolInfo(kind, (C.c_uint32 * 3)(*pos), radius, (C.c_uint32 * 3)(*src), (C.c_uint32 * 3)(*dst))
+            oc, _ = hdo.trace_colors(odag, ocol, paths, 0, 0, oti, True)
+            assert np.array_equal(oc, want), f"tool {kind} dag {dk}: oracle differs in {(oc != want).sum()} pixels"
+            hit_overlay += int((want != plain).sum())
+    assert hit_overlay > 1000, "the overlay never showed"
+    t.close()
+    rt.close()
