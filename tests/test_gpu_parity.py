@@ -269,3 +269,31 @@ def test_beam_prepass_never_changes_a_pixel(levels, fp, w, h, kind):
         assert np.array_equal(frames[1][1], osh)
     assert resumed > 0, "the beam pre-pass never took over a tile"
     t.close()
+
+
+def test_replay_file_drives_the_tracer_like_the_engine(tr, tmp_path):
+    """hashdag_b200/replay.py: a camera track written in the reference's replay CSV format, read back and run
+    through resolve_paths / resolve_colors / resolve_shadows per frame; stats rows as the reference reports them."""
+    from hashdag_b200 import replay, tracer
+    s = get_scene(13, 10)
+    t = tr(13)
+    dag, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
+    cams = scene_cameras(s, 3, 10)[:4]
+    path = str(tmp_path / "track.csv")
+    replay.dump([replay.Frame(c) for c in cams], path)
+    frames = replay.load(path)
+    assert len(frames) == 4
+    stats = replay.run(t, frames, _info(s), dag, col, 1.0, 0.0)
+    last = t.read_colors()
+    rows = replay.StatsRecorder.read_csv(stats.to_csv(str(tmp_path / "track.stats.csv")))
+    assert [r[1] for r in rows] == ["paths", "colors", "shadows"] * 4 and all(r[2] > 0 for r in rows) and rows[-1][0] == 3
+    # std::to_string keeps 6 decimals: the replayed camera is the written one rounded, and the frame is its frame
+    cam = frames[-1].camera
+    t.resolve_paths(cam, _info(s), dag); t.resolve_colors(dag, col); t.resolve_shadows(cam, _info(s), dag, 1.0, 0.0)
+    assert np.array_equal(t.read_colors(), last)
+    odag, ocol = hdo.make_dag(s, hdo.DAG_HASH), hdo.make_colors(s, hdo.COLORS_HASH)
+    prm = camera.trace_params(cam, _info(s), 13, W, H)
+    op, _ = hdo.trace_paths(odag, W, H, prm)
+    oc, _ = hdo.trace_colors(odag, ocol, op)
+    osh, _ = hdo.trace_shadows(odag, prm, op, oc, 1.0, 0.0)
+    assert np.array_equal(last, osh)
