@@ -8,7 +8,10 @@
 #include <cstring>
 #include <string>
 
+#include <vector>
+
 #include "hdt_beam.cuh"
+#include "hdt_color_leaf.cuh"
 #include "hdt_colors.cuh"
 #include "hdt_device.cuh"
 
@@ -22,6 +25,7 @@ static_assert(sizeof(hdt_basic_uncompressed_colors) == 40, "BasicDAGUncompressed
 static_assert(sizeof(hdt_basic_color_errors) == 288, "BasicDAGColorErrors layout");
 static_assert(sizeof(hdt_hash_colors) == 248, "HashDAGColors layout");
 static_assert(sizeof(hdt_tool_info) == 44, "ToolInfo layout");
+static_assert(sizeof(hdt_color_op) == 32, "hdt_color_op layout");
 
 namespace {
 
@@ -416,6 +420,8 @@ struct hdt_ctx {
     u32 beamMaxVisits = 32;
     u32 beamTag = 0;                    // bumped per beam launch; per-ray kernels ignore states of other launches
     int lastBeamPass = 0;
+    void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, colour stream, per-macro-block sums (grow-only)
+    size_t rebuildScratchBytes = 0;
 
     RayPlanes ray_planes(int pass) const { return RayPlanes{ rays[pass], buffer_pixels() }; }
 
@@ -738,6 +744,7 @@ int hdt_destroy(hdt_ctx* c)
     for (auto& e : c->timer) if (e) cudaEventDestroy(e);
     cudaFree(c->hitCounter);
     cudaFree(c->tables);
+    cudaFree(c->rebuildScratch);
     if (c->side) cudaStreamSynchronize(c->side);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->beams[i]); cudaFree(c->seeds[i]); cudaFree(c->rays[i]);
@@ -1043,6 +1050,88 @@ int hdt_apply_ranges(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload_dev,
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));
     HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t old_leaf_size, const hdt_color_op* ops, uint64_t n_ops,
+                           uint32_t* weights_out, uint64_t weights_capacity, uint64_t* blocks_out, uint64_t blocks_capacity,
+                           uint64_t* macro_blocks_out, uint64_t macro_blocks_capacity, uint64_t counts_out[4], float* ms)
+{
+    if (!c || (!ops && n_ops) || !counts_out) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: null argument");
+    if (old_leaf && old_leaf_size != sizeof(hdt_color_leaf)) return fail(HDT_ERR_POD_SIZE, "CompressedColorLeaf: expected 104 bytes");
+    if (ms) *ms = 0.f;
+    // op list -> device form: empty ops dropped, exclusive prefix of the counts, one sentinel
+    std::vector<ColorOpDev> dev;
+    dev.reserve(n_ops + 1);
+    u64 n = 0;
+    bool copies = false;
+    for (u64 i = 0; i < n_ops; ++i) {
+        const hdt_color_op& o = ops[i];
+        if (o.kind != HDT_COLOR_OP_COPY && o.kind != HDT_COLOR_OP_FILL) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: unknown op kind");
+        if (o.kind == HDT_COLOR_OP_FILL && (o.bits_per_weight > 4 || (o.bits_per_weight && o.weight >> o.bits_per_weight) || (!o.bits_per_weight && o.weight)))
+            return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: weight does not fit bits_per_weight (0..4)");
+        if (!o.count) continue;
+        copies |= o.kind == HDT_COLOR_OP_COPY;
+        dev.push_back(ColorOpDev{ n, o.src_start, o.kind, o.bits_per_weight, o.color_bits, o.weight });
+        n += o.count;
+    }
+    counts_out[0] = n; counts_out[1] = counts_out[2] = counts_out[3] = 0;
+    if (n == 0) return HDT_OK;
+    if (n >= (u64(1) << 30)) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: more colours than the reference's 32-bit weight offsets can address");
+    if (dev.size() >= (u64(1) << 32) - 1) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: too many ops");
+    ColorLeafDev leaf{};
+    if (copies) {
+        if (!old_leaf || !old_leaf->blocks_gpu.data || !old_leaf->macro_blocks_gpu.data) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: COPY ops need the old leaf");
+        leaf = leaf_dev(*old_leaf);
+    }
+    dev.push_back(ColorOpDev{ n, 0, HDT_COLOR_OP_FILL, 0, 0, 0 });
+    const u32 nTiles = u32((n + kColorsPerMacroBlock - 1) / kColorsPerMacroBlock);
+    HDT_CUDA(cudaSetDevice(c->device));
+    // scratch: [ops][stream, padded to whole macro blocks][tile pairs][tile offsets][totals]
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t offOps = 0, offStream = align(dev.size() * sizeof(ColorOpDev)), offTiles = offStream + align(size_t(nTiles) * kColorsPerMacroBlock * 8);
+    const size_t offOffsets = offTiles + align(size_t(nTiles) * sizeof(TilePair)), offTotals = offOffsets + align(size_t(nTiles) * sizeof(ulonglong2));
+    const size_t need = offTotals + 256;
+    if (need > c->rebuildScratchBytes) {
+        HDT_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->rebuildScratch); c->rebuildScratch = nullptr; c->rebuildScratchBytes = 0;
+        HDT_CUDA(cudaMalloc(&c->rebuildScratch, need + need / 2));
+        c->rebuildScratchBytes = need + need / 2;
+    }
+    char* base = static_cast<char*>(c->rebuildScratch);
+    ColorOpDev* dOps = reinterpret_cast<ColorOpDev*>(base + offOps);
+    u64* dStream = reinterpret_cast<u64*>(base + offStream);
+    TilePair* dTiles = reinterpret_cast<TilePair*>(base + offTiles);
+    ulonglong2* dOffsets = reinterpret_cast<ulonglong2*>(base + offOffsets);
+    u64* dTotals = reinterpret_cast<u64*>(base + offTotals);
+    HDT_CUDA(cudaMemcpyAsync(dOps, dev.data(), dev.size() * sizeof(ColorOpDev), cudaMemcpyHostToDevice, c->stream));
+    HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    expand_color_ops_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, dStream, dTiles);
+    scan_color_tiles_kernel<<<1, 1024, 0, c->stream>>>(dTiles, nTiles, dOffsets, dTotals);
+    HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    c->launches += 2;
+    u64 totals[2] = { 0, 0 };
+    HDT_CUDA(cudaMemcpyAsync(totals, dTotals, sizeof(totals), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    if (totals[1] >= (u64(1) << 32)) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: weight stream beyond the reference's 32-bit bit offsets");
+    counts_out[1] = (totals[1] + 31) / 32; counts_out[2] = totals[0]; counts_out[3] = 2 * u64(nTiles);
+    if (counts_out[1] > weights_capacity || counts_out[2] > blocks_capacity || counts_out[3] > macro_blocks_capacity)
+        return fail(HDT_ERR_CAPACITY, "hdt_rebuild_color_leaf: an output buffer is too small (see counts_out)");
+    if ((counts_out[1] && !weights_out) || !blocks_out || !macro_blocks_out) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: null output buffer");
+    HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if (counts_out[1]) HDT_CUDA(cudaMemsetAsync(weights_out, 0, counts_out[1] * sizeof(u32), c->stream));
+    emit_color_leaf_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dStream, n, dOffsets, weights_out, blocks_out, macro_blocks_out);
+    HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    ++c->launches;
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    if (ms) {
+        float a = 0.f, b = 0.f;
+        HDT_CUDA(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+        HDT_CUDA(cudaEventElapsedTime(&b, c->ev[2], c->ev[3]));
+        *ms = a + b;
+    }
     return HDT_OK;
 }
 

@@ -35,8 +35,9 @@ EXPORTS = (
     "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_set_option", "hdt_beam_stats", "hdt_pass_timeline", "hdt_resolve_paths", "hdt_resolve_colors",
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
-    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_launch_count", "hdt_version",
+    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_rebuild_color_leaf", "hdt_launch_count", "hdt_version",
 )
+ERR_CAPACITY = 4
 
 
 class TracerError(RuntimeError):
@@ -86,6 +87,8 @@ def load_library():
     lib.hdt_assemble_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hdt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.hdt_apply_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.hdt_rebuild_color_leaf.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                           C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), fp]
     lib.hdt_launch_count.restype = C.c_uint64
     lib.hdt_launch_count.argtypes = [C.c_void_p]
     _lib = lib
@@ -369,6 +372,29 @@ class DAGTracer:
     def apply_ranges(self, dst_tensor, payload_tensor, ranges_tensor, n_ranges: int):
         """dst[r.dst_word + i] = payload[r.src_word + i] for every hdt_range r (edit-dirtied spans, see edits.py)."""
         _check(self._lib.hdt_apply_ranges(self._ctx, dst_tensor.data_ptr(), payload_tensor.data_ptr(), ranges_tensor.data_ptr(), n_ranges))
+
+    def rebuild_color_leaf(self, ops: np.ndarray, old_leaf: "CompressedColorLeaf | None" = None, device=None):
+        """Re-encode a colour leaf on the GPU from an op list (color_leaf.OP_DTYPE records = hdt_color_op), see
+        hashdag_b200/color_leaf.py.  -> (CompressedColorLeaf with device tensors, kernel ms)."""
+        torch = _torch()
+        device = device or f"cuda:{self.device}"
+        ops = np.ascontiguousarray(ops)
+        assert ops.dtype.itemsize == 32, "ops must be hdt_color_op records"
+        n = int(ops["count"].sum()) if ops.size else 0
+        counts = (C.c_uint64 * 4)()
+        pod = old_leaf.pod() if old_leaf is not None else None
+        if n == 0:
+            return CompressedColorLeaf(None, None, None, UNIQUE_OFFSET), 0.0
+        # worst case: every colour its own block with 4-bit weights (12.5 B / colour); trimmed below
+        blocks = torch.empty(n, dtype=torch.int64, device=device)
+        macro = torch.empty(2 * ((n + 16383) // 16384), dtype=torch.int64, device=device)
+        weights = torch.empty((4 * n + 31) // 32, dtype=torch.int32, device=device)
+        _check(self._lib.hdt_rebuild_color_leaf(self._ctx, pod, len(pod) if pod else 0, ops.ctypes.data, ops.size, weights.data_ptr(), weights.numel(),
+                                                blocks.data_ptr(), blocks.numel(), macro.data_ptr(), macro.numel(), counts, C.byref(self._ms)))
+        assert counts[0] == n
+        nw, nb, nm = int(counts[1]), int(counts[2]), int(counts[3])
+        leaf = CompressedColorLeaf(weights[:nw].clone() if nw else None, blocks[:nb].clone(), macro[:nm].clone(), UNIQUE_OFFSET)
+        return leaf, self._ms.value
 
     def set_stream(self, cuda_stream_handle):
         """Enqueue on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""

@@ -36,7 +36,7 @@ enum {
 enum { HDT_DEBUG_NONE = 0, HDT_DEBUG_INDEX, HDT_DEBUG_POSITION, HDT_DEBUG_COLOR_TREE, HDT_DEBUG_COLOR_BITS,
        HDT_DEBUG_MIN_COLOR, HDT_DEBUG_MAX_COLOR, HDT_DEBUG_WEIGHT };
 
-enum { HDT_OK = 0, HDT_ERR_ARG = 1, HDT_ERR_POD_SIZE = 2, HDT_ERR_STATE = 3, HDT_ERR_CUDA = 1000 };
+enum { HDT_OK = 0, HDT_ERR_ARG = 1, HDT_ERR_POD_SIZE = 2, HDT_ERR_STATE = 3, HDT_ERR_CAPACITY = 4, HDT_ERR_CUDA = 1000 };
 
 /* ---- POD mirrors (device pointers unless the field says _cpu) ------------------------------ */
 typedef struct hdt_array { const void* data; uint64_t size; } hdt_array;                       /* StaticArray<T>,  array.h:8-129  */
@@ -77,6 +77,19 @@ typedef struct hdt_tool_info {                                                  
 } hdt_tool_info;
 
 typedef struct hdt_range { uint64_t dst_word; uint64_t src_word; uint64_t n_words; } hdt_range; /* one dirty span, hash_table.cpp:129-180 */
+
+/* One step of a colour-leaf rebuild, in voxel order: what the editor hands to ColorLeafBuilder while it walks an
+ * edited colour leaf (hash_dag_edits.h:381-396, :430-437, :488-516). */
+enum {
+    HDT_COLOR_OP_COPY = 0,  /* CompressedColorLeaf::copy_colors (vwsc.h:416-542): `count` colours of the old leaf starting at its
+                               colour `src_start` (the editor's oldLeavesCount; a shared leaf's offset is added by the library) */
+    HDT_COLOR_OP_FILL = 1   /* `count` times ColorLeafBuilder::add(color) (vwsc.h:582-613); with bits_per_weight == 0 this is
+                               add_large_single_color (vwsc.h:614-641) */
+};
+typedef struct hdt_color_op {
+    uint64_t src_start; uint64_t count; uint32_t kind;
+    uint32_t bits_per_weight; uint32_t color_bits; uint32_t weight;   /* CompressedColor (vwsc.h:86-90), FILL only */
+} hdt_color_op;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
 /* Replaces DAGTracer::DAGTracer(headLess=true) (dag_tracer.cu:9-45); width/height/levels are
@@ -172,6 +185,20 @@ int hdt_assemble_colors(hdt_ctx* ctx, const uint32_t* gathered_dev, uint32_t* fr
 int hdt_set_stream(hdt_ctx* ctx, void* cuda_stream);
 /* Apply edit-dirtied spans to a replica: dst[range.dst_word + i] = payload[range.src_word + i]. */
 int hdt_apply_ranges(hdt_ctx* ctx, uint32_t* dst_dev, const uint32_t* payload_dev, const hdt_range* ranges_dev, uint32_t n_ranges);
+
+/* ---- next to the path: colour-leaf rebuild ------------------------------------ */
+/* Replaces ColorLeafBuilder::add / add_large_single_color / build (vwsc.h:549-721) fed by
+ * CompressedColorLeaf::copy_colors (vwsc.h:416-542), i.e. the re-encoding of a colour leaf an edit touched
+ * (hash_dag.h:384-398).  `ops` (HOST memory) lists, in voxel order, what the new leaf is made of; `old_leaf`
+ * (device arrays; may be NULL when there is no COPY op) is the leaf being replaced.  The three output arrays are
+ * DEVICE buffers owned by the caller; worst-case sizes for n = sum of counts colours are n blocks, 2*ceil(n/16384)
+ * macro-block words and ceil(4n/32) weight words.  counts_out = {colours, weight words, blocks, macro-block words}
+ * actually produced (HOST); the arrays are bit-identical to weights_CPU / blocks_CPU / macroBlocks_CPU after
+ * ColorLeafBuilder::build.  HDT_ERR_CAPACITY (counts_out filled in, nothing written) if a buffer is too small.
+ * Synchronous; ms = device time of the kernels. */
+int hdt_rebuild_color_leaf(hdt_ctx* ctx, const hdt_color_leaf* old_leaf, size_t old_leaf_size, const hdt_color_op* ops, uint64_t n_ops,
+                           uint32_t* weights_out, uint64_t weights_capacity, uint64_t* blocks_out, uint64_t blocks_capacity,
+                           uint64_t* macro_blocks_out, uint64_t macro_blocks_capacity, uint64_t counts_out[4], float* ms);
 
 /* Kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t hdt_launch_count(const hdt_ctx* ctx);

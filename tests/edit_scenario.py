@@ -13,8 +13,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 import golden_util as gu                      # noqa: E402
+import make_color_leaf_golden as mk           # noqa: E402
 from hashdag_b200 import camera, edits, tracer   # noqa: E402
 from oracle import hdo, ref                   # noqa: E402
 
@@ -47,8 +49,8 @@ def main(recipe="d13"):
     h0 = float(scene.heights[(int(c), int(c))])
     poses = gu.recipe_poses(scene)[:2] + [camera.look_at((c - 60.0, h0 + 45.0, c - 50.0), (c + 10.0, h0, c + 5.0))]
     # shaped like replays/replay_edits_add.csv / _remove.csv: spheres of mixed radii on the surface, added then carved
-    plan = [((c + 20.5, h0 + 6.0, c + 10.5), 12.0, True), ((c - 15.0, h0 - 2.0, c + 5.0), 9.0, False), ((c + 3.0, h0 + 14.0, c - 8.0), 3.0, True),
-            ((c + 18.0, h0 + 9.0, c + 12.0), 7.0, False), ((c - 30.0, h0 + 4.0, c - 22.0), 25.0, True), ((c - 28.0, h0 + 10.0, c - 20.0), 14.0, False)]
+    # (radii 3-25 at depth 13, 10-60 at depth 17)
+    plan = mk.leaf_plan(scene)
     leaves_host = []
     report = []
     for k, (centre, radius, adding) in enumerate(plan):

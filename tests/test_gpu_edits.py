@@ -14,10 +14,11 @@ from oracle import ref
 pytestmark = pytest.mark.gpu
 
 
-def test_frames_follow_the_reference_through_a_sequence_of_edits():
-    if not ref.available(13, 256, 256):
+@pytest.mark.parametrize("recipe", ["d13", "d17"])
+def test_frames_follow_the_reference_through_a_sequence_of_edits(recipe):
+    if not ref.available(int(recipe[1:]), 256, 256):
         pytest.skip("oracle/_ref variant not built")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "edit_scenario.py"), "d13"], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "edit_scenario.py"), recipe], capture_output=True, text=True, timeout=900)
     line = [l for l in r.stdout.splitlines() if l.startswith("EDIT_SCENARIO ")]
     assert line, r.stdout[-2000:] + r.stderr[-4000:]
     report = json.loads(line[-1][len("EDIT_SCENARIO "):])
