@@ -11,13 +11,17 @@
 //     colour; its header holds the weight bit offset and colour index RELATIVE to the macro block;
 //   * weights are appended MSB-first to a bit stream kept in 32-bit words, each byte-swapped by build().
 // None of this depends on more than the previous colour and two prefix sums, so the device version is:
-//   1. expand_color_ops_kernel   one CTA per macro block, one thread per 16 consecutive colours: evaluate the op
-//                                list (copy from the old leaf = its get_color, or a constant colour), write the
-//                                colour stream (8 B / colour), reduce {blocks, weight bits} per macro block;
+//   1. count_color_ops_kernel    one CTA per macro block of the NEW leaf, one thread per 16 consecutive colours:
+//                                evaluate the op list (copy from the old leaf, or a constant colour) and reduce
+//                                {blocks started, weight bits} per macro block;
 //   2. scan_color_tiles_kernel   exclusive scan of those pairs (one CTA; a leaf has n/16384 macro blocks);
-//   3. emit_color_leaf_kernel    one CTA per macro block: CTA-wide scan, block headers, macro-block pairs, and
-//                                the weight bits assembled in shared memory and stored as whole swapped words
-//                                (the two words a macro block may share with its neighbours go through atomicOr).
+//   3. emit_color_leaf_kernel    one CTA per macro block: evaluate the ops again, CTA-wide scan, block headers,
+//                                macro-block pairs, and the weight bits assembled in shared memory and stored as
+//                                whole swapped words (the two words a macro block may share with its neighbours
+//                                go through atomicOr).
+// The colours are evaluated twice rather than staged in memory: a thread reads the old leaf like copy_colors does
+// (one binary search, then a walk along the blocks), which costs a few cached loads per colour, whereas a staged
+// stream would be 16 B of HBM traffic per colour against ~1.5 B of algorithmic bytes (old leaf in, new leaf out).
 // Bit-exact with the reference builder by construction; pinned against leaves the reference built
 // (tests/golden/ref_color_leaves_d13.npz, tests/test_gpu_color_leaf.py).
 #pragma once
@@ -86,45 +90,118 @@ __device__ __forceinline__ void thread_flags(const u64 (&c)[kColorsPerThread], u
     nBlocks = __popc(flags);
 }
 
-__global__ void __launch_bounds__(kRebuildThreads) expand_color_ops_kernel(const ColorOpDev* __restrict__ ops, const u32 nOps, const ColorLeafDev oldLeaf,
-                                                                             const u64 nColors, u64* __restrict__ stream, TilePair* __restrict__ tiles)
+// Walks the old leaf like CompressedColorLeaf::copy_colors (vwsc.h:462-540): binary_search_blocks once, then block by
+// block and macro block by macro block.
+struct LeafCursor {
+    u32 macro, block, lastBlock, nextStart;   // nextStart: local colour index where the next block of this macro block starts
+    u32 hdr, colorBits, bpw;
+    u64 macroWeightOffset;
+
+    __device__ __forceinline__ void load_block(const ColorLeafDev& l)
+    {
+        const u64 b = __ldg(l.blocks + block);
+        hdr = u32(b); colorBits = u32(b >> 32);
+        bpw = ((hdr >> 16) == 0xFFFF) ? 0u : (((hdr >> 14) & 0x3) + 1);
+        nextStart = block < lastBlock ? (u32(__ldg(l.blocks + block + 1)) & 0x3FFF) : u32(kColorsPerMacroBlock);
+    }
+    __device__ __forceinline__ void load_macro(const ColorLeafDev& l)
+    {
+        lastBlock = (2 * (u64(macro) + 1) < l.nMacroWords) ? u32(__ldg(l.macroBlocks + 2 * (macro + 1)) - 1) : u32(l.nBlocks - 1);
+        macroWeightOffset = __ldg(l.macroBlocks + 2 * macro + 1);
+    }
+    // position on colour `colorIndex` (absolute: the shared leaf's offset already added), vwsc.h:343-372
+    __device__ __forceinline__ void seek(const ColorLeafDev& l, u64 colorIndex)
+    {
+        const u32 local = u32(colorIndex % kColorsPerMacroBlock);
+        macro = u32(colorIndex / kColorsPerMacroBlock);
+        load_macro(l);
+        u32 lo = u32(__ldg(l.macroBlocks + 2 * macro)), hi = lastBlock;
+        u32 pos = (lo + hi) / 2;
+        u32 idx = u32(__ldg(l.blocks + pos)) & 0x3FFF;
+        while (idx != local && lo <= hi) {
+            if (idx > local) hi = pos - 1; else lo = pos + 1;
+            pos = (lo + hi) / 2;
+            idx = u32(__ldg(l.blocks + pos)) & 0x3FFF;
+        }
+        block = pos;
+        load_block(l);
+    }
+    // colour `local` of the current macro block (the cursor stands on its block), vwsc.h:374-403
+    __device__ __forceinline__ u64 color(const ColorLeafDev& l, u32 local) const
+    {
+        u32 weight = 0;
+        if (bpw) {
+            const u64 bitPtr = macroWeightOffset + (hdr >> 16) + u64(local - (hdr & 0x3FFF)) * bpw;
+            const u8* bytes = reinterpret_cast<const u8*>(l.weights) + (bitPtr >> 3);
+            const u32 be16 = (u32(__ldg(bytes)) << 8) | u32(__ldg(bytes + 1));
+            weight = (be16 >> (16 - bpw - u32(bitPtr & 7))) & ((1u << bpw) - 1);
+        }
+        return pack_color(colorBits, bpw, weight);
+    }
+    // step from colour `local` to `local + 1` (vwsc.h:497-520); returns the new local index
+    __device__ __forceinline__ u32 advance(const ColorLeafDev& l, u32 local)
+    {
+        if (++local == kColorsPerMacroBlock) {
+            ++macro; ++block; local = 0;
+            load_macro(l);
+            load_block(l);
+        } else if (local >= nextStart) {
+            ++block;
+            load_block(l);
+        }
+        return local;
+    }
+};
+
+// The 16 consecutive colours [first, first + nValid) of the new leaf, from the op list.
+__device__ __forceinline__ void eval_ops(const ColorOpDev* __restrict__ ops, const u32 nOps, const ColorLeafDev& oldLeaf, const u64 first, const u32 nValid,
+                                         u64 (&c)[kColorsPerThread])
+{
+#pragma unroll
+    for (u32 j = 0; j < kColorsPerThread; ++j) c[j] = 0;
+    if (!nValid) return;
+    // op of the first colour: last op with dstStart <= first (ops[nOps].dstStart = nColors is a sentinel)
+    u32 lo = 0, hi = nOps - 1;
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (__ldg(&ops[mid].dstStart) <= first) lo = mid; else hi = mid - 1;
+    }
+    ColorOpDev op = ops[lo];
+    u64 opEnd = __ldg(&ops[lo + 1].dstStart);
+    LeafCursor cur;
+    u32 local = 0;
+    bool seeked = false;
+#pragma unroll
+    for (u32 j = 0; j < kColorsPerThread; ++j) {
+        if (j < nValid) {
+            const u64 i = first + j;
+            while (i >= opEnd) { ++lo; op = ops[lo]; opEnd = __ldg(&ops[lo + 1].dstStart); seeked = false; }
+            if (op.kind == HDT_COLOR_OP_COPY) {
+                if (!seeked) {
+                    const u64 src = op.srcStart + (i - op.dstStart) + (oldLeaf.is_shared() ? oldLeaf.offset : 0);
+                    cur.seek(oldLeaf, src);
+                    local = u32(src % kColorsPerMacroBlock);
+                    seeked = true;
+                } else {
+                    local = cur.advance(oldLeaf, local);
+                }
+                c[j] = cur.color(oldLeaf, local);
+            } else {
+                c[j] = pack_color(op.colorBits, op.bitsPerWeight, op.weight);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRebuildThreads) count_color_ops_kernel(const ColorOpDev* __restrict__ ops, const u32 nOps, const ColorLeafDev oldLeaf,
+                                                                            const u64 nColors, TilePair* __restrict__ tiles)
 {
     __shared__ u64 lastKey[kRebuildThreads];
     const u64 first = u64(blockIdx.x) * kColorsPerMacroBlock + u64(threadIdx.x) * kColorsPerThread;
     const u32 nValid = first >= nColors ? 0u : u32(min(u64(kColorsPerThread), nColors - first));
     u64 c[kColorsPerThread];
-    if (nValid) {
-        // op of the first colour: last op with dstStart <= first (ops[nOps].dstStart = nColors is a sentinel)
-        u32 lo = 0, hi = nOps - 1;
-        while (lo < hi) {
-            const u32 mid = (lo + hi + 1) >> 1;
-            if (__ldg(&ops[mid].dstStart) <= first) lo = mid; else hi = mid - 1;
-        }
-        ColorOpDev op = ops[lo];
-        u64 opEnd = __ldg(&ops[lo + 1].dstStart);
-#pragma unroll
-        for (u32 j = 0; j < kColorsPerThread; ++j) {
-            c[j] = 0;
-            if (j < nValid) {
-                const u64 i = first + j;
-                while (i >= opEnd) { ++lo; op = ops[lo]; opEnd = __ldg(&ops[lo + 1].dstStart); }
-                if (op.kind == HDT_COLOR_OP_COPY) {
-                    const CompressedColorDev cc = leaf_get_color(oldLeaf, op.srcStart + (i - op.dstStart));
-                    c[j] = pack_color(cc.colorBits, cc.bitsPerWeight, cc.weight);
-                } else {
-                    c[j] = pack_color(op.colorBits, op.bitsPerWeight, op.weight);
-                }
-            }
-        }
-    } else {
-#pragma unroll
-        for (u32 j = 0; j < kColorsPerThread; ++j) c[j] = 0;
-    }
+    eval_ops(ops, nOps, oldLeaf, first, nValid, c);
     lastKey[threadIdx.x] = c[kColorsPerThread - 1] & kBlockKeyMask;
-    // the stream is padded to whole macro blocks: every thread stores its 128 bytes
-    ulonglong2* dst = reinterpret_cast<ulonglong2*>(stream + first);
-#pragma unroll
-    for (u32 j = 0; j < kColorsPerThread; j += 2) dst[j / 2] = make_ulonglong2(c[j], c[j + 1]);
     __syncthreads();
     u32 flags, nBlocks, nBits;
     thread_flags(c, nValid, threadIdx.x == 0, threadIdx.x ? lastKey[threadIdx.x - 1] : 0, flags, nBlocks, nBits);
@@ -157,9 +234,11 @@ __device__ __forceinline__ u32 make_block_header(u32 weightOffset, u32 bitsPerWe
     return (weightOffset << 16) | (bitsPerWeight << 14) | index;
 }
 
-__global__ void __launch_bounds__(kRebuildThreads) emit_color_leaf_kernel(const u64* __restrict__ stream, const u64 nColors, const ulonglong2* __restrict__ offsets,
+__global__ void __launch_bounds__(kRebuildThreads) emit_color_leaf_kernel(const ColorOpDev* __restrict__ ops, const u32 nOps, const ColorLeafDev oldLeaf,
+                                                                            const u64 nColors, const ulonglong2* __restrict__ offsets,
                                                                             u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
 {
+    __shared__ u64 lastKey[kRebuildThreads];
     // a macro block holds at most 16384 * 4 weight bits = 2048 words, + 1 for the misaligned start, + 1 so that a
     // straddling store of the last weight stays in bounds
     __shared__ u32 words[kColorsPerMacroBlock * 4 / 32 + 2];
@@ -167,12 +246,11 @@ __global__ void __launch_bounds__(kRebuildThreads) emit_color_leaf_kernel(const 
     const u32 nValid = first >= nColors ? 0u : u32(min(u64(kColorsPerThread), nColors - first));
     for (u32 k = threadIdx.x; k < sizeof(words) / 4; k += blockDim.x) words[k] = 0;
     u64 c[kColorsPerThread];
-    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(stream + first);
-#pragma unroll
-    for (u32 j = 0; j < kColorsPerThread; j += 2) { const ulonglong2 v = src[j / 2]; c[j] = v.x; c[j + 1] = v.y; }
-    const u64 prevKey = threadIdx.x ? (stream[first - 1] & kBlockKeyMask) : 0;
+    eval_ops(ops, nOps, oldLeaf, first, nValid, c);
+    lastKey[threadIdx.x] = c[kColorsPerThread - 1] & kBlockKeyMask;
+    __syncthreads();
     u32 flags, nBlocks, nBits;
-    thread_flags(c, nValid, threadIdx.x == 0, prevKey, flags, nBlocks, nBits);
+    thread_flags(c, nValid, threadIdx.x == 0, threadIdx.x ? lastKey[threadIdx.x - 1] : 0, flags, nBlocks, nBits);
     u64 total;
     const u64 excl = cta_exclusive_scan((u64(nBlocks) << 32) | nBits, total);   // also orders the zeroing of `words` before the atomics
     const ulonglong2 tile = offsets[blockIdx.x];

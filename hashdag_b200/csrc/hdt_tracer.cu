@@ -420,7 +420,7 @@ struct hdt_ctx {
     u32 beamMaxVisits = 32;
     u32 beamTag = 0;                    // bumped per beam launch; per-ray kernels ignore states of other launches
     int lastBeamPass = 0;
-    void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, colour stream, per-macro-block sums (grow-only)
+    void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, per-macro-block sums (grow-only)
     size_t rebuildScratchBytes = 0;
 
     RayPlanes ray_planes(int pass) const { return RayPlanes{ rays[pass], buffer_pixels() }; }
@@ -1071,6 +1071,13 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
         if (o.kind == HDT_COLOR_OP_FILL && (o.bits_per_weight > 4 || (o.bits_per_weight && o.weight >> o.bits_per_weight) || (!o.bits_per_weight && o.weight)))
             return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: weight does not fit bits_per_weight (0..4)");
         if (!o.count) continue;
+        if (o.kind == HDT_COLOR_OP_COPY) {
+            // the old leaf addresses whole macro blocks (the length of its last block is not stored)
+            const u64 have = old_leaf ? (old_leaf->macro_blocks_gpu.size / 2) * kColorsPerMacroBlock : 0;
+            const u64 off = (old_leaf && old_leaf->offset != kUniqueOffset) ? old_leaf->offset : 0;
+            if (off > have || o.src_start > have - off || o.count > have - off - o.src_start)
+                return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: COPY op reaches beyond the old leaf's macro blocks");
+        }
         copies |= o.kind == HDT_COLOR_OP_COPY;
         dev.push_back(ColorOpDev{ n, o.src_start, o.kind, o.bits_per_weight, o.color_bits, o.weight });
         n += o.count;
@@ -1087,9 +1094,9 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     dev.push_back(ColorOpDev{ n, 0, HDT_COLOR_OP_FILL, 0, 0, 0 });
     const u32 nTiles = u32((n + kColorsPerMacroBlock - 1) / kColorsPerMacroBlock);
     HDT_CUDA(cudaSetDevice(c->device));
-    // scratch: [ops][stream, padded to whole macro blocks][tile pairs][tile offsets][totals]
+    // scratch: [ops][tile pairs][tile offsets][totals]
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
-    const size_t offOps = 0, offStream = align(dev.size() * sizeof(ColorOpDev)), offTiles = offStream + align(size_t(nTiles) * kColorsPerMacroBlock * 8);
+    const size_t offOps = 0, offTiles = align(dev.size() * sizeof(ColorOpDev));
     const size_t offOffsets = offTiles + align(size_t(nTiles) * sizeof(TilePair)), offTotals = offOffsets + align(size_t(nTiles) * sizeof(ulonglong2));
     const size_t need = offTotals + 256;
     if (need > c->rebuildScratchBytes) {
@@ -1100,13 +1107,12 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     }
     char* base = static_cast<char*>(c->rebuildScratch);
     ColorOpDev* dOps = reinterpret_cast<ColorOpDev*>(base + offOps);
-    u64* dStream = reinterpret_cast<u64*>(base + offStream);
     TilePair* dTiles = reinterpret_cast<TilePair*>(base + offTiles);
     ulonglong2* dOffsets = reinterpret_cast<ulonglong2*>(base + offOffsets);
     u64* dTotals = reinterpret_cast<u64*>(base + offTotals);
     HDT_CUDA(cudaMemcpyAsync(dOps, dev.data(), dev.size() * sizeof(ColorOpDev), cudaMemcpyHostToDevice, c->stream));
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    expand_color_ops_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, dStream, dTiles);
+    count_color_ops_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, dTiles);
     scan_color_tiles_kernel<<<1, 1024, 0, c->stream>>>(dTiles, nTiles, dOffsets, dTotals);
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->launches += 2;
@@ -1121,7 +1127,7 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     if ((counts_out[1] && !weights_out) || !blocks_out || !macro_blocks_out) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: null output buffer");
     HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (counts_out[1]) HDT_CUDA(cudaMemsetAsync(weights_out, 0, counts_out[1] * sizeof(u32), c->stream));
-    emit_color_leaf_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dStream, n, dOffsets, weights_out, blocks_out, macro_blocks_out);
+    emit_color_leaf_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, dOffsets, weights_out, blocks_out, macro_blocks_out);
     HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));
