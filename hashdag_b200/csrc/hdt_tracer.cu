@@ -14,6 +14,7 @@
 #include "hdt_color_leaf.cuh"
 #include "hdt_colors.cuh"
 #include "hdt_device.cuh"
+#include "hdt_region.cuh"
 
 using namespace hdt;
 
@@ -1138,6 +1139,75 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
         HDT_CUDA(cudaEventElapsedTime(&b, c->ev[2], c->ev[3]));
         *ms = a + b;
     }
+    return HDT_OK;
+}
+
+int hdt_get_values(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, const uint32_t start[3], const uint32_t size[3],
+                   uint8_t* values_dev, float* ms)
+{
+    if (!c || !start || !size) return fail(HDT_ERR_ARG, "hdt_get_values: null argument");
+    if (ms) *ms = 0.f;
+    DagArg dag;
+    if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, dag)) return rc;
+    RegionParams rp;
+    for (int a = 0; a < 3; ++a) {
+        rp.start[a] = start[a]; rp.size[a] = size[a];
+        if (!size[a]) return HDT_OK;                       // nothing to write
+        if (u64(start[a]) + size[a] > (u64(1) << c->levels)) return fail(HDT_ERR_ARG, "hdt_get_values: region beyond the DAG's 2^levels voxels");
+        rp.cell0[a] = start[a] >> 2;
+        rp.nCells[a] = ((start[a] + size[a] - 1) >> 2) - rp.cell0[a] + 1;
+    }
+    if (!values_dev) return fail(HDT_ERR_ARG, "hdt_get_values: null output");
+    const u64 nCells = u64(rp.nCells[0]) * rp.nCells[1] * rp.nCells[2];
+    if ((nCells + 127) / 128 > 0x7FFFFFFFull) return fail(HDT_ERR_ARG, "hdt_get_values: region too large for one launch");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    const u32 grid = u32((nCells + 127) / 128);
+    if (dag.kind == HDT_DAG_BASIC) get_values_kernel<<<grid, 128, 0, c->stream>>>(dag.basic, c->levels, rp, values_dev);
+    else get_values_kernel<<<grid, 128, 0, c->stream>>>(dag.hash, c->levels, rp, values_dev);
+    HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    ++c->launches;
+    return finish_timed(c, c->ev[0], c->ev[1], ms);
+}
+
+int hdt_is_empty(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_size, uint32_t max_level, const uint32_t start[3],
+                 const uint32_t size[3], int* empty, float* ms)
+{
+    if (!c || !start || !size || !empty) return fail(HDT_ERR_ARG, "hdt_is_empty: null argument");
+    if (ms) *ms = 0.f;
+    if (max_level > c->levels - 2) return fail(HDT_ERR_ARG, "hdt_is_empty: max_level must be <= levels - 2 (dag_utils.h:264)");
+    DagArg dag;
+    if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, dag)) return rc;
+    if (max_level == 0) { *empty = 0; return HDT_OK; }    // the recursion returns false at the root (dag_utils.h:185-188)
+    // nodes of level max_level-1 are cells of 2^shift voxels; candidates: bmin < start+size and bmin + 2^shift - 1 > start
+    const u32 steps = max_level - 1, shift = c->levels - steps;
+    RegionParams rp;
+    for (int a = 0; a < 3; ++a) {
+        rp.start[a] = start[a]; rp.size[a] = size[a];
+        const u64 inMax = u64(start[a]) + size[a];
+        if (inMax > (u64(1) << c->levels)) return fail(HDT_ERR_ARG, "hdt_is_empty: region beyond the DAG's 2^levels voxels");
+        if (inMax == 0) { *empty = 1; return HDT_OK; }
+        const u64 lo = (u64(start[a]) + 1) >> shift, hi = (inMax - 1) >> shift;
+        if (lo > hi || lo >= (u64(1) << steps)) { *empty = 1; return HDT_OK; }
+        rp.cell0[a] = u32(lo);
+        rp.nCells[a] = u32(hi - lo + 1);
+    }
+    const u64 nCells = u64(rp.nCells[0]) * rp.nCells[1] * rp.nCells[2];
+    if ((nCells + 127) / 128 > 0x7FFFFFFFull) return fail(HDT_ERR_ARG, "hdt_is_empty: region too large for one launch");
+    HDT_CUDA(cudaSetDevice(c->device));
+    u32* found = reinterpret_cast<u32*>(c->hitCounter);
+    HDT_CUDA(cudaMemsetAsync(found, 0, sizeof(u32), c->stream));
+    HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    const u32 grid = u32((nCells + 127) / 128);
+    if (dag.kind == HDT_DAG_BASIC) is_empty_kernel<<<grid, 128, 0, c->stream>>>(dag.basic, steps, rp, found);
+    else is_empty_kernel<<<grid, 128, 0, c->stream>>>(dag.hash, steps, rp, found);
+    HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    ++c->launches;
+    u32 host = 0;
+    HDT_CUDA(cudaMemcpyAsync(&host, found, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    if (int rc = finish_timed(c, c->ev[0], c->ev[1], ms)) return rc;
+    *empty = host ? 0 : 1;
     return HDT_OK;
 }
 

@@ -35,7 +35,7 @@ EXPORTS = (
     "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_set_option", "hdt_beam_stats", "hdt_pass_timeline", "hdt_resolve_paths", "hdt_resolve_colors",
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
-    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_rebuild_color_leaf", "hdt_launch_count", "hdt_version",
+    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_version",
 )
 ERR_CAPACITY = 4
 
@@ -89,6 +89,9 @@ def load_library():
     lib.hdt_apply_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.hdt_rebuild_color_leaf.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                            C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), fp]
+    u3 = C.POINTER(C.c_uint32)
+    lib.hdt_get_values.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, u3, u3, C.c_void_p, fp]
+    lib.hdt_is_empty.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_uint32, u3, u3, C.POINTER(C.c_int), fp]
     lib.hdt_launch_count.restype = C.c_uint64
     lib.hdt_launch_count.argtypes = [C.c_void_p]
     _lib = lib
@@ -395,6 +398,24 @@ class DAGTracer:
         nw, nb, nm = int(counts[1]), int(counts[2]), int(counts[3])
         leaf = CompressedColorLeaf(weights[:nw].clone() if nw else None, blocks[:nb].clone(), macro[:nm].clone(), UNIQUE_OFFSET)
         return leaf, self._ms.value
+
+    # -- region queries of the copy tool (DAGUtils, dag_utils.h:175-411) -------------------------
+    def get_values(self, dag, start, size):
+        """DAGUtils::get_values: -> (uint8 device tensor [size.z, size.y, size.x], kernel ms)."""
+        torch = _torch()
+        out = torch.empty((int(size[2]), int(size[1]), int(size[0])), dtype=torch.uint8, device=f"cuda:{self.device}")
+        pod = dag.pod()
+        u3 = lambda v: (C.c_uint32 * 3)(*[int(x) for x in v])
+        _check(self._lib.hdt_get_values(self._ctx, dag.kind, pod, len(pod), u3(start), u3(size), out.data_ptr(), C.byref(self._ms)))
+        return out, self._ms.value
+
+    def is_empty(self, dag, max_level: int, start, size) -> bool:
+        """DAGUtils::is_empty(dag, maxLevel, start, size)."""
+        pod = dag.pod()
+        u3 = lambda v: (C.c_uint32 * 3)(*[int(x) for x in v])
+        e = C.c_int()
+        _check(self._lib.hdt_is_empty(self._ctx, dag.kind, pod, len(pod), int(max_level), u3(start), u3(size), C.byref(e), C.byref(self._ms)))
+        return bool(e.value)
 
     def set_stream(self, cuda_stream_handle):
         """Enqueue on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""

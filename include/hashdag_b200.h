@@ -200,6 +200,18 @@ int hdt_rebuild_color_leaf(hdt_ctx* ctx, const hdt_color_leaf* old_leaf, size_t 
                            uint32_t* weights_out, uint64_t weights_capacity, uint64_t* blocks_out, uint64_t blocks_capacity,
                            uint64_t* macro_blocks_out, uint64_t macro_blocks_capacity, uint64_t counts_out[4], float* ms);
 
+/* ---- next to the path: region queries of the copy tool -------------------------- */
+/* DAGUtils::get_values (dag_utils.h:268-411): values_dev[x + size.x*(y + size.y*z)] (DEVICE, one byte per voxel, all
+ * size.x*size.y*size.z of them written) = 1 iff voxel start+(x,y,z) exists and x, y, z > 0 -- the reference's box
+ * test (dag_utils.h:278-296) is strict on the low side, so the three planes through `start` stay 0.
+ * Synchronous; ms = device time. */
+int hdt_get_values(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size, const uint32_t start[3], const uint32_t size[3],
+                   uint8_t* values_dev, float* ms);
+/* DAGUtils::is_empty (dag_utils.h:175-266), max_level <= levels-2 like its checkAlways: *empty = 0 iff max_level == 0 or
+ * a node of level max_level-1 exists whose voxel box [bmin, bmax] has bmin < start+size and bmax > start on every axis. */
+int hdt_is_empty(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size, uint32_t max_level, const uint32_t start[3],
+                 const uint32_t size[3], int* empty, float* ms);
+
 /* Kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t hdt_launch_count(const hdt_ctx* ctx);
 int hdt_version(void);

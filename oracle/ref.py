@@ -63,6 +63,10 @@ class RefTracer:
             l.ref_color_leaf_copy.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
             l.ref_resolve_colors_tool.restype = C.c_float
             l.ref_resolve_colors_tool.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, u3, C.c_float, u3, u3]
+        if hasattr(l, "ref_get_values"):
+            u3 = C.POINTER(C.c_uint32)
+            l.ref_get_values.argtypes = [u3, u3, C.c_void_p]
+            l.ref_is_empty.argtypes = [C.c_uint32, u3, u3]
         if l.ref_init(device) != 0:
             raise RuntimeError("ref_init failed (no CUDA device?)")
         self.scene = None
@@ -121,6 +125,19 @@ class RefTracer:
             assert self.lib.ref_color_leaf_copy(i, w.ctypes.data, bl.ctypes.data, m.ctypes.data) == 0
             out.append((w, bl, m))
         return out
+
+    def get_values(self, start, size):
+        """DAGUtils::get_values<5> on the reference's HashDAG (host walk) -> uint8[size.z, size.y, size.x]."""
+        u3 = lambda v: (C.c_uint32 * 3)(*[int(x) for x in v])
+        out = np.full((int(size[2]), int(size[1]), int(size[0])), 0xAA, dtype=np.uint8)
+        assert self.lib.ref_get_values(u3(start), u3(size), out.ctypes.data) == 0
+        return out
+
+    def is_empty(self, max_level, start, size):
+        u3 = lambda v: (C.c_uint32 * 3)(*[int(x) for x in v])
+        r = self.lib.ref_is_empty(int(max_level), u3(start), u3(size))
+        assert r in (0, 1)
+        return bool(r)
 
     def tool_overlay_compiled(self):
         return bool(self.lib.ref_tool_overlay_compiled())

@@ -49,5 +49,19 @@ int ref_color_leaf_copy(uint64_t i, uint32_t* weights, uint64_t* blocks, uint64_
     return 0;
 }
 
+// The copy tool's read-only walks over the (possibly edited) HashDAG, on the host like the reference runs them
+// (hash_dag_editors.h:401, :476, :570): DAGUtils::get_values<5> (dag_utils.h:363-411) and DAGUtils::is_empty (:255-266).
+int ref_get_values(const uint32_t* start, const uint32_t* size, uint8_t* values)
+{
+    if (!g_hasHash) return 1;
+    static_assert(sizeof(bool) == 1, "values are bytes");
+    DAGUtils::get_values<5>(g_hash, reinterpret_cast<bool*>(values), make_uint3(start[0], start[1], start[2]), make_uint3(size[0], size[1], size[2]));
+    return 0;
+}
+int ref_is_empty(uint32_t maxLevel, const uint32_t* start, const uint32_t* size)
+{
+    if (!g_hasHash) return -1;
+    return DAGUtils::is_empty(g_hash, maxLevel, make_uint3(start[0], start[1], start[2]), make_uint3(size[0], size[1], size[2])) ? 1 : 0;
+}
 
 }  // extern "C"
