@@ -421,6 +421,9 @@ struct hdt_ctx {
     u32 beamMaxVisits = 32;
     u32 beamTag = 0;                    // bumped per beam launch; per-ray kernels ignore states of other launches
     int lastBeamPass = 0;
+    char* stagingHost = nullptr;        // hdt_apply_ranges_host: pinned + device staging, bump-allocated, reset when full
+    char* stagingDev = nullptr;
+    size_t stagingCap = 0, stagingUsed = 0;
     void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, per-macro-block sums (grow-only)
     size_t rebuildScratchBytes = 0;
 
@@ -746,6 +749,8 @@ int hdt_destroy(hdt_ctx* c)
     cudaFree(c->hitCounter);
     cudaFree(c->tables);
     cudaFree(c->rebuildScratch);
+    if (c->stagingHost) cudaFreeHost(c->stagingHost);
+    cudaFree(c->stagingDev);
     if (c->side) cudaStreamSynchronize(c->side);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->beams[i]); cudaFree(c->seeds[i]); cudaFree(c->rays[i]);
@@ -1050,6 +1055,42 @@ int hdt_apply_ranges(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload_dev,
     apply_ranges_kernel<<<n_ranges < 1184 ? n_ranges : 1184, 128, 0, c->stream>>>(dst_dev, payload_dev, ranges_dev, n_ranges);
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+int hdt_apply_ranges_host(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload_host, uint64_t n_payload_words, const hdt_range* ranges_host, uint32_t n_ranges)
+{
+    if (!c || !dst_dev || (!ranges_host && n_ranges) || (!payload_host && n_payload_words)) return fail(HDT_ERR_ARG, "hdt_apply_ranges_host: null argument");
+    if (!n_ranges) return HDT_OK;
+    for (u32 i = 0; i < n_ranges; ++i)
+        if (ranges_host[i].src_word > n_payload_words || ranges_host[i].n_words > n_payload_words - ranges_host[i].src_word)
+            return fail(HDT_ERR_ARG, "hdt_apply_ranges_host: a range reads beyond the payload");
+    HDT_CUDA(cudaSetDevice(c->device));
+    const size_t rangeBytes = (size_t(n_ranges) * sizeof(hdt_range) + 255) & ~size_t(255);
+    const size_t need = rangeBytes + ((size_t(n_payload_words) * 4 + 255) & ~size_t(255));
+    if (c->stagingUsed + need > c->stagingCap) {
+        HDT_CUDA(cudaStreamSynchronize(c->stream));           // everything staged so far has been consumed
+        c->stagingUsed = 0;
+        if (need > c->stagingCap) {
+            const size_t cap = need * 2 > (size_t(8) << 20) ? need * 2 : (size_t(8) << 20);
+            if (c->stagingHost) cudaFreeHost(c->stagingHost);
+            cudaFree(c->stagingDev);
+            c->stagingHost = nullptr; c->stagingDev = nullptr; c->stagingCap = 0;
+            HDT_CUDA(cudaMallocHost(&c->stagingHost, cap));
+            HDT_CUDA(cudaMalloc(&c->stagingDev, cap));
+            c->stagingCap = cap;
+        }
+    }
+    char* h = c->stagingHost + c->stagingUsed;
+    char* d = c->stagingDev + c->stagingUsed;
+    memcpy(h, ranges_host, size_t(n_ranges) * sizeof(hdt_range));
+    memcpy(h + rangeBytes, payload_host, size_t(n_payload_words) * 4);
+    HDT_CUDA(cudaMemcpyAsync(d, h, need, cudaMemcpyHostToDevice, c->stream));
+    c->stagingUsed += need;
+    apply_ranges_kernel<<<n_ranges < 1184 ? n_ranges : 1184, 128, 0, c->stream>>>(dst_dev, reinterpret_cast<const u32*>(d + rangeBytes),
+                                                                                 reinterpret_cast<const hdt_range*>(d), n_ranges);
+    ++c->launches;
     HDT_CUDA(cudaGetLastError());
     return HDT_OK;
 }

@@ -107,6 +107,81 @@ def diff_hash_dag(old_pool, old_table, new_pool, new_table, first_node_index, po
 
 
 # ---------------------------------------------------------------------------------------------
+# the dirty tracker proper: what grew since the last upload, from the hash table's own bookkeeping
+# ---------------------------------------------------------------------------------------------
+class HashLayout:
+    """Virtual address space of the reference's HashTable (hash_dag_globals.h:7-38 with the defaults of
+    typedefs.h:201-236): levels 0-8 have 1024 buckets of 1024 words, deeper levels 65536 buckets of 4096 words;
+    `bucket_base[i]` = HashDagUtils::make_ptr(level, bucket, 0) (hash_table.h:45-63) of global bucket i
+    (get_bucket_global_index, hash_table.h:18-35)."""
+    PAGE = 512
+
+    def __init__(self, levels, top_levels=9, top_bits=10, low_bits=16, top_size=1024, low_size=4096):
+        n_top = min(top_levels, levels) << top_bits
+        n_low = max(levels - top_levels, 0) << low_bits
+        self.levels, self.n_buckets = levels, n_top + n_low
+        self.bucket_base = np.concatenate((np.arange(n_top, dtype=np.int64) * top_size, n_top * top_size + np.arange(n_low, dtype=np.int64) * low_size))
+        self.n_pages = int((n_top * top_size + n_low * low_size) // self.PAGE)
+
+
+def delta_from_bucket_sizes(layout: HashLayout, last_sizes, sizes, cpu_pool, page_table, first_node_index, pool_top, merge_gap: int = 32) -> "DagDelta":
+    """The pool / page-table part of a delta WITHOUT comparing the arrays: the hash table only ever appends to its
+    buckets, so what changed since the last upload is, per bucket, the words between its size then and now -- the very
+    walk of HashTable::upload_to_gpu (hash_table.cpp:158-183).  `cpu_pool` / `page_table` are the host arrays (physical
+    layout == the GPU pool's under MANUAL_VIRTUAL_MEMORY, hash_table.cpp:137-141).  O(#buckets) instead of O(pool)."""
+    last_sizes = np.asarray(last_sizes)
+    sizes = np.asarray(sizes)
+    grown = np.flatnonzero(sizes != last_sizes)
+    if grown.size == 0:
+        e = np.zeros(0, dtype=RANGE_DTYPE)
+        return DagDelta(int(first_node_index), int(pool_top), e, np.zeros(0, np.uint32), e.copy(), np.zeros(0, np.uint32))
+    P = layout.PAGE
+    start = layout.bucket_base[grown] + last_sizes[grown].astype(np.int64)     # virtual pointers
+    end = layout.bucket_base[grown] + sizes[grown].astype(np.int64)
+    assert (end > start).all(), "a bucket shrank: not an append-only edit (undo / GC are outside the tracker)"
+    # split at page boundaries: a bucket spans at most low_size / PAGE pages
+    first_page, last_page = start // P, (end - 1) // P
+    n_pieces = (last_page - first_page + 1)
+    idx = np.repeat(np.arange(grown.size), n_pieces)
+    page = np.repeat(first_page, n_pieces) + (np.arange(n_pieces.sum()) - np.repeat(np.cumsum(n_pieces) - n_pieces, n_pieces))
+    lo = np.maximum(start[idx], page * P)
+    hi = np.minimum(end[idx], (page + 1) * P)
+    phys = page_table[page].astype(np.int64) * P + (lo - page * P)
+    order = np.argsort(phys, kind="stable")
+    phys, n = phys[order], (hi - lo)[order]
+    # merge neighbouring pieces (gap <= merge_gap words: the words in between are unchanged on both sides)
+    brk = np.flatnonzero(phys[1:] - (phys[:-1] + n[:-1]) > merge_gap) + 1
+    s = np.concatenate(([0], brk))
+    e = np.concatenate((brk, [phys.size]))
+    d0, d1 = phys[s], (phys + n)[e - 1]
+    ranges = np.zeros(s.size, dtype=RANGE_DTYPE)
+    ranges["dst_word"], ranges["n_words"] = d0, d1 - d0
+    ranges["src_word"] = np.concatenate(([0], np.cumsum(d1 - d0)[:-1]))
+    payload = np.concatenate([cpu_pool[a:b] for a, b in zip(d0.tolist(), d1.tolist())]).astype(np.uint32, copy=False)
+    # page table: the entries of every touched page (rewriting an unchanged entry is harmless)
+    pages = np.unique(page)
+    pb = np.flatnonzero(np.diff(pages) > 1) + 1
+    ps, pe = np.concatenate(([0], pb)), np.concatenate((pb, [pages.size]))
+    tr = np.zeros(ps.size, dtype=RANGE_DTYPE)
+    tr["dst_word"], tr["n_words"] = pages[ps], pages[pe - 1] - pages[ps] + 1
+    tr["src_word"] = np.concatenate(([0], np.cumsum(tr["n_words"])[:-1]))
+    tp = np.concatenate([page_table[a:b + 1] for a, b in zip(pages[ps].tolist(), pages[pe - 1].tolist())]).astype(np.uint32, copy=False)
+    return DagDelta(int(first_node_index), int(pool_top), ranges, payload, tr, tp)
+
+
+def add_color_delta(d: "DagDelta", old_color_nodes, new_color_nodes, old_leaves, new_leaves) -> "DagDelta":
+    """Colour part of a delta (tree nodes + rebuilt unique leaves), as in diff_hash_dag."""
+    d.color_node_ranges, d.color_node_payload = dirty_spans(old_color_nodes if old_color_nodes is not None else np.zeros(0, np.uint32), new_color_nodes)
+    d.n_color_nodes = int(new_color_nodes.size)
+    old_leaves = old_leaves or []
+    d.n_color_leaves = len(new_leaves)
+    for i, leaf in enumerate(new_leaves):
+        if not leaf.same_as(old_leaves[i] if i < len(old_leaves) else None):
+            d.color_leaves[i] = leaf
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
 # shipping a delta to the other ranks
 # ---------------------------------------------------------------------------------------------
 def broadcast_delta(delta: DagDelta | None, src: int = 0, device="cpu") -> DagDelta:
@@ -179,36 +254,57 @@ class HashDagReplica:
             self.main_leaf = main_leaf                  # tracer.CompressedColorLeaf on this device
             self.leaves = {}                            # index -> tracer.CompressedColorLeaf (keeps the tensors alive)
             self.leaf_pods = None                       # int64 tensor, 13 words per leaf (CompressedColorLeaf, 104 B)
+            self._pods_host = None                      # the same on the host, updated row by row
 
     def apply(self, delta: DagDelta) -> None:
+        """Enqueue the delta on the tracer's stream (hdt_apply_ranges_host: staged through pinned memory, no host
+        synchronisation for the pool / page table / colour tree); new colour leaves go up as ONE packed buffer."""
         T, torch = self._T, self._torch
         if int(delta.pool_top) * 512 > self.pool.numel():
             raise T.TracerError("HashDagReplica: the edit outgrew the replica's pool capacity")
-
-        def spans(dst, ranges, payload):
-            if len(ranges):
-                self.tracer.apply_ranges(dst, T._to_device(payload, self.device), torch.from_numpy(ranges.view(np.int64).reshape(-1, 3).copy()).to(self.device), len(ranges))
-        spans(self.pool, delta.pool_ranges, delta.pool_payload)
-        spans(self.page_table, delta.table_ranges, delta.table_payload)
+        self.tracer.apply_ranges_host(self.pool, delta.pool_payload, delta.pool_ranges)
+        self.tracer.apply_ranges_host(self.page_table, delta.table_payload, delta.table_ranges)
         self.pool_top, self.first_node_index = int(delta.pool_top), int(delta.first_node_index)
         if self.has_colors and delta.n_color_nodes:
             if delta.n_color_nodes > self.color_nodes.numel():
                 grown = torch.zeros(2 * delta.n_color_nodes, dtype=torch.int32, device=self.device)
-                grown[: self.color_nodes.numel()] = self.color_nodes
                 self.tracer.sync()
+                grown[: self.color_nodes.numel()] = self.color_nodes
+                torch.cuda.synchronize()
                 self.color_nodes = grown
-            spans(self.color_nodes, delta.color_node_ranges, delta.color_node_payload)
+            self.tracer.apply_ranges_host(self.color_nodes, delta.color_node_payload, delta.color_node_ranges)
             self.n_color_nodes = delta.n_color_nodes
-            for i, l in delta.color_leaves.items():
-                self.leaves[i] = T.CompressedColorLeaf(T._to_device(l.weights, self.device), T._to_device(l.blocks, self.device),
-                                                       T._to_device(l.macro_blocks, self.device), T.UNIQUE_OFFSET)
-            if delta.n_color_leaves:
-                pods = np.zeros((delta.n_color_leaves, 13), dtype=np.uint64)
-                for i in range(delta.n_color_leaves):
-                    if i in self.leaves:
-                        pods[i] = np.frombuffer(self.leaves[i].pod(), dtype=np.uint64)
+            if delta.color_leaves:
+                # one packed upload for every new / rebuilt leaf of this edit; the leaves are views into it
+                ids = sorted(delta.color_leaves)
+                parts, offs, total = [], [], 0
+                for i in ids:
+                    l = delta.color_leaves[i]
+                    for a in (l.blocks, l.macro_blocks, l.weights):          # 8-byte arrays first: every part stays aligned
+                        b = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+                        offs.append((total, a.size))
+                        parts.append(b)
+                        total += (b.size + 7) // 8 * 8
+                flat = np.zeros(total, dtype=np.uint8)
+                for (o, _), b in zip(offs, parts):
+                    flat[o:o + b.size] = b
+                buf = torch.from_numpy(flat).to(self.device)
+                for k, i in enumerate(ids):
+                    (ob, nb), (om, nm), (ow, nw) = offs[3 * k: 3 * k + 3]
+                    blocks = buf[ob: ob + 8 * nb].view(torch.int64) if nb else None
+                    macro = buf[om: om + 8 * nm].view(torch.int64) if nm else None
+                    weights = buf[ow: ow + 4 * nw].view(torch.int32) if nw else None
+                    self.leaves[i] = T.CompressedColorLeaf(weights, blocks, macro, T.UNIQUE_OFFSET)
+            if delta.n_color_leaves and (delta.color_leaves or self._pods_host is None or self._pods_host.shape[0] != delta.n_color_leaves):
+                if self._pods_host is None or self._pods_host.shape[0] < delta.n_color_leaves:
+                    grown = np.zeros((delta.n_color_leaves, 13), dtype=np.uint64)
+                    if self._pods_host is not None:
+                        grown[: self._pods_host.shape[0]] = self._pods_host
+                    self._pods_host = grown
+                for i in delta.color_leaves:
+                    self._pods_host[i] = np.frombuffer(self.leaves[i].pod(), dtype=np.uint64)
                 self.tracer.sync()                      # frames in flight may still read the previous POD array
-                self.leaf_pods = T._to_device(pods.reshape(-1), self.device)
+                self.leaf_pods = T._to_device(self._pods_host[: delta.n_color_leaves].reshape(-1), self.device)
 
     def dag(self):
         return self._T.HashDAG(self.pool, self.page_table, self.pool_top, self.first_node_index, self.levels)

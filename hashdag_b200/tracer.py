@@ -35,7 +35,7 @@ EXPORTS = (
     "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_set_option", "hdt_beam_stats", "hdt_pass_timeline", "hdt_resolve_paths", "hdt_resolve_colors",
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
-    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_version",
+    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_version",
 )
 ERR_CAPACITY = 4
 
@@ -87,6 +87,7 @@ def load_library():
     lib.hdt_assemble_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hdt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.hdt_apply_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.hdt_apply_ranges_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     lib.hdt_rebuild_color_leaf.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                            C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), fp]
     u3 = C.POINTER(C.c_uint32)
@@ -375,6 +376,15 @@ class DAGTracer:
     def apply_ranges(self, dst_tensor, payload_tensor, ranges_tensor, n_ranges: int):
         """dst[r.dst_word + i] = payload[r.src_word + i] for every hdt_range r (edit-dirtied spans, see edits.py)."""
         _check(self._lib.hdt_apply_ranges(self._ctx, dst_tensor.data_ptr(), payload_tensor.data_ptr(), ranges_tensor.data_ptr(), n_ranges))
+
+    def apply_ranges_host(self, dst_tensor, payload: np.ndarray, ranges: np.ndarray):
+        """hdt_apply_ranges with host arrays (uint32 payload, hdt_range records): staged and applied in stream order, no sync."""
+        if len(ranges) == 0:
+            return
+        payload = np.ascontiguousarray(payload)
+        ranges = np.ascontiguousarray(ranges)
+        assert payload.dtype.itemsize == 4 and ranges.dtype.itemsize == 24
+        _check(self._lib.hdt_apply_ranges_host(self._ctx, dst_tensor.data_ptr(), payload.ctypes.data, payload.size, ranges.ctypes.data, len(ranges)))
 
     def rebuild_color_leaf(self, ops: np.ndarray, old_leaf: "CompressedColorLeaf | None" = None, device=None):
         """Re-encode a colour leaf on the GPU from an op list (color_leaf.OP_DTYPE records = hdt_color_op), see

@@ -212,6 +212,14 @@ int hdt_get_values(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_p
 int hdt_is_empty(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size, uint32_t max_level, const uint32_t start[3],
                  const uint32_t size[3], int* empty, float* ms);
 
+/* hdt_apply_ranges with `ranges` and `payload` in HOST memory (pageable is fine): both are staged through pinned memory
+ * owned by the context, copied and applied in stream order.  Returns once the copy and the kernel are enqueued --
+ * frames enqueued afterwards see the edit, no host synchronisation is involved (hdt_sync() reports errors).
+ * Replaces the page-table memcpy + one cudaMemcpyAsync per grown bucket of HashTable::upload_to_gpu
+ * (hash_table.cpp:120-184) and its closing cudaDeviceSynchronize. */
+int hdt_apply_ranges_host(hdt_ctx* ctx, uint32_t* dst_dev, const uint32_t* payload_host, uint64_t n_payload_words,
+                          const hdt_range* ranges_host, uint32_t n_ranges);
+
 /* Kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t hdt_launch_count(const hdt_ctx* ctx);
 int hdt_version(void);

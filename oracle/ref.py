@@ -63,6 +63,11 @@ class RefTracer:
             l.ref_color_leaf_copy.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
             l.ref_resolve_colors_tool.restype = C.c_float
             l.ref_resolve_colors_tool.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, u3, C.c_float, u3, u3]
+        if hasattr(l, "ref_hash_pointers"):
+            l.ref_hash_pointers.argtypes = [C.POINTER(C.c_uint64)] * 3 + [C.POINTER(C.c_uint32)]
+        if hasattr(l, "ref_last_edit_ms"):
+            l.ref_last_edit_ms.argtypes = [C.POINTER(C.c_double)]
+            l.ref_last_edit_ms.restype = None
         if hasattr(l, "ref_get_values"):
             u3 = C.POINTER(C.c_uint32)
             l.ref_get_values.argtypes = [u3, u3, C.c_void_p]
@@ -78,7 +83,7 @@ class RefTracer:
             self.lib.ref_shutdown()
             self.lib = None
 
-    def load_scene(self, scene, with_hash=True, with_colors=True, with_uncompressed=False):
+    def load_scene(self, scene, with_hash=True, with_colors=True, with_uncompressed=False, extra_pool_pages=4096):
         assert scene.levels == self.depth
         l = self.lib
         self.scene = scene
@@ -92,7 +97,8 @@ class RefTracer:
                                           scene.uncompressed.ctypes.data, scene.uncompressed.size)
         if with_hash:
             hash_colors = with_colors and scene.levels - 2 > 10
-            l.ref_build_hash_dag(scene.hash_pool_top + 4096, int(hash_colors))
+            self._pool_pages = scene.hash_pool_top + int(extra_pool_pages)
+            l.ref_build_hash_dag(self._pool_pages, int(hash_colors))
 
     def hash_dag(self):
         """(pool, page_table, first_node_index, pool_top) as built by the reference's own factory."""
@@ -102,6 +108,22 @@ class RefTracer:
         pt = np.empty(s.value, dtype=np.uint32)
         self.lib.ref_hash_copy(pool.ctypes.data, pt.ctypes.data)
         return pool, pt, f.value, t.value
+
+    def hash_views(self):
+        """Zero-copy numpy views of the reference's HOST arrays: (pool[:capacity], page_table, bucket_sizes).  They alias
+        live memory: the next edit changes them in place."""
+        p, t, b, n = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+        assert self.lib.ref_hash_pointers(C.byref(p), C.byref(t), C.byref(b), C.byref(n)) == 0
+        f, top, size = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        assert self.lib.ref_hash_info(C.byref(f), C.byref(top), C.byref(size)) == 0
+        view = lambda addr, count: np.ctypeslib.as_array(C.cast(addr.value, C.POINTER(C.c_uint32)), shape=(count,))
+        return view(p, self._pool_pages * 512), view(t, size.value), view(b, n.value)
+
+    def hash_info(self):
+        """(first_node_index, pool_top)"""
+        f, top, size = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        assert self.lib.ref_hash_info(C.byref(f), C.byref(top), C.byref(size)) == 0
+        return f.value, top.value
 
     def hash_colors(self):
         a, b = C.c_uint64(), C.c_uint64()
@@ -114,6 +136,12 @@ class RefTracer:
     def edit_sphere(self, center, radius, adding):
         """The reference's own CPU edit (SphereEditor<adding>, hash_dag_editors.h:273-313) + upload_to_gpu."""
         assert self.lib.ref_edit_sphere(float(center[0]), float(center[1]), float(center[2]), float(radius), int(bool(adding))) == 0
+
+    def last_edit_ms(self):
+        """(HashDAG::edit_threads, HashTable::upload_to_gpu) host milliseconds of the last edit_sphere."""
+        out = (C.c_double * 2)()
+        self.lib.ref_last_edit_ms(out)
+        return float(out[0]), float(out[1])
 
     def color_leaves(self):
         """Unique colour leaves created by edits: list of (weights, blocks, macro_blocks)."""

@@ -133,6 +133,17 @@ int ref_hash_copy(uint32_t* pool, uint32_t* pageTable)
     std::memcpy(pageTable, HashTable::cpuData.cpuPageTable, size_t(g_hash.data.pageTableSize) * sizeof(uint32));
     return 0;
 }
+// Zero-copy access for the host-side dirty tracker (hashdag_b200/edits.py): the reference's own host arrays and the
+// per-bucket fill counts its upload_to_gpu walks (hash_table.cpp:160-183).
+int ref_hash_pointers(uint64_t* pool, uint64_t* pageTable, uint64_t* bucketSizes, uint32_t* nBuckets)
+{
+    if (!g_hasHash) return 1;
+    *pool = reinterpret_cast<uint64_t>(HashTable::cpuData.cpuPool);
+    *pageTable = reinterpret_cast<uint64_t>(HashTable::cpuData.cpuPageTable);
+    *bucketSizes = reinterpret_cast<uint64_t>(HashTable::cpuData.bucketsSizes);
+    *nBuckets = C_totalNumberOfBuckets;
+    return 0;
+}
 int ref_hash_colors_info(uint64_t* nNodes, uint64_t* nOffsets)
 {
     if (!g_hasHashColors) return 1;

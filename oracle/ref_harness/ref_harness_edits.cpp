@@ -10,6 +10,8 @@ using namespace refh;
 namespace {
 HashDAGUndoRedo g_undoRedo;
 StatsRecorder g_statsRecorder;
+double g_lastEditMs = 0, g_lastUploadMs = 0;   // harness stopwatch around the reference's two calls
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }
 
 extern "C" {
@@ -19,6 +21,7 @@ extern "C" {
 int ref_edit_sphere(float x, float y, float z, float radius, int adding)
 {
     if (!g_hasHash || !g_hasHashColors) return 1;
+    const double t0 = now_ms();
     if (adding) {
         const auto tool = SphereEditor<true>(make_float3(x, y, z), radius);
         g_hash.edit_threads(tool, g_hashColors, g_undoRedo, g_statsRecorder);
@@ -26,9 +29,15 @@ int ref_edit_sphere(float x, float y, float z, float radius, int adding)
         const auto tool = SphereEditor<false>(make_float3(x, y, z), radius);
         g_hash.edit_threads(tool, g_hashColors, g_undoRedo, g_statsRecorder);
     }
+    const double t1 = now_ms();
     g_hash.data.upload_to_gpu();
+    cudaDeviceSynchronize();
+    g_lastEditMs = t1 - t0; g_lastUploadMs = now_ms() - t1;
     return 0;
 }
+// Host wall time of the last ref_edit_sphere: [0] HashDAG::edit_threads (includes its colour-leaf rebuilds and their
+// uploads, hash_dag.h:384-398), [1] HashTable::upload_to_gpu (hash_table.cpp:120-184).
+void ref_last_edit_ms(double* out) { out[0] = g_lastEditMs; out[1] = g_lastUploadMs; }
 
 // Unique colour leaves created by edits (HashDAGColors::leaves, hash_dag_colors.h:65-73).
 uint64_t ref_color_leaf_count() { return g_hasHashColors ? g_hashColors.leaves_CPU.size() : 0; }

@@ -53,12 +53,20 @@ def main(recipe="d13"):
     plan = mk.leaf_plan(scene)
     leaves_host = []
     report = []
+    layout = edits.HashLayout(scene.levels)
+    vpool, vtable, vsizes = rt.hash_views()          # the reference's live host arrays + per-bucket fill counts
+    assert vsizes.size == layout.n_buckets and vtable.size == layout.n_pages
+    last_sizes = vsizes.copy()
     for k, (centre, radius, adding) in enumerate(plan):
         rt.edit_sphere(centre, radius, adding)
         npool, ntable, nfirst, ntop = rt.hash_dag()
         nnodes, _ = rt.hash_colors()
         nleaves = [edits.ColorLeafArrays(*l) for l in rt.color_leaves()]
-        delta = edits.diff_hash_dag(pool, table, npool, ntable, nfirst, ntop, nodes, nnodes, leaves_host, nleaves)
+        full = edits.diff_hash_dag(pool, table, npool, ntable, nfirst, ntop, nodes, nnodes, leaves_host, nleaves)
+        # the product path: spans from the hash table's own bookkeeping, no array comparison (edits.delta_from_bucket_sizes)
+        delta = edits.add_color_delta(edits.delta_from_bucket_sizes(layout, last_sizes, vsizes, vpool, vtable, nfirst, ntop), nodes, nnodes, leaves_host, nleaves)
+        last_sizes = vsizes.copy()
+        assert delta.pool_payload.size <= 2 * full.pool_payload.size + 64 * max(1, len(delta.pool_ranges))
         # host mirror of the device apply: the delta alone reproduces the new arrays
         hp = np.zeros(max(pool.size, ntop * 512), np.uint32); hp[: pool.size] = pool
         edits.apply_spans_host(hp, delta.pool_ranges, delta.pool_payload)

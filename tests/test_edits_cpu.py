@@ -82,3 +82,43 @@ def test_replicas_follow_an_edit_through_one_broadcast(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "ok0.npy"), np.load(tmp_path / "ok1.npy")
     assert r0[0] == 1 and r1[0] == 1 and r0[1] == r1[1] > 0
+
+
+def _grow(rng, layout, sizes, table, pool, top, n_buckets_to_grow):
+    """Append random words to random buckets of a fake hash table, allocating physical pages on demand (hash_table.h:416-442)."""
+    P = layout.PAGE
+    cap = np.where(np.arange(layout.n_buckets) < (min(9, layout.levels) << 10), 1024, 4096)
+    for b in rng.choice(layout.n_buckets, n_buckets_to_grow, replace=False):
+        add = int(rng.integers(1, 700))
+        add = min(add, int(cap[b] - sizes[b]))
+        for k in range(add):
+            v = int(layout.bucket_base[b] + sizes[b] + k)
+            if table[v // P] == 0:
+                table[v // P] = top
+                top += 1
+            pool[int(table[v // P]) * P + v % P] = rng.integers(1, 2 ** 32)
+        sizes[b] += add
+    return top
+
+
+def test_bucket_size_tracker_reproduces_the_arrays_without_comparing_them():
+    rng = np.random.default_rng(21)
+    layout = edits.HashLayout(13)
+    assert layout.n_buckets == 9 * 1024 + 4 * 65536 and layout.bucket_base[9 * 1024] == 9 * 1024 * 1024
+    sizes = np.zeros(layout.n_buckets, np.uint32)
+    table = np.zeros(layout.n_pages, np.uint32)
+    pool = np.zeros(2000 * 512, np.uint32)
+    top = _grow(rng, layout, sizes, table, pool, 1, 250)            # physical page 0 stays unused (hash_table.h:821)
+    dev_pool, dev_table, last = pool.copy(), table.copy(), sizes.copy()
+    for step in range(3):
+        top = _grow(rng, layout, sizes, table, pool, top, 70)
+        d = edits.delta_from_bucket_sizes(layout, last, sizes, pool, table, first_node_index=7, pool_top=top)
+        full = edits.diff_hash_dag(dev_pool, dev_table, pool, table, 7, top)
+        edits.apply_spans_host(dev_pool, d.pool_ranges, d.pool_payload)
+        edits.apply_spans_host(dev_table, d.table_ranges, d.table_payload)
+        assert np.array_equal(dev_pool, pool) and np.array_equal(dev_table, table)
+        assert d.pool_payload.size < 1.5 * full.pool_payload.size + 64 * len(d.pool_ranges)    # a delta of the same order as the exact diff
+        assert int(d.pool_ranges["n_words"].sum()) == d.pool_payload.size and int(d.table_ranges["n_words"].sum()) == d.table_payload.size
+        last = sizes.copy()
+    none = edits.delta_from_bucket_sizes(layout, sizes, sizes, pool, table, 7, top)
+    assert len(none.pool_ranges) == 0 and len(none.table_ranges) == 0
