@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dag", default="hash", choices=["hash", "basic"])
     ap.add_argument("--no-beam-prefetch", action="store_true", help="keep the beam kernels of frame n+1 behind all of frame n")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the tiles reach rank 0's frame -- stores over peer memory (hdt_exchange_*, default) or NCCL gather + assembly (A/B)")
     ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
                     help="tracer contexts (each with its own streams and frame buffers) the fly-through alternates between")
     return ap.parse_args()
@@ -163,7 +165,7 @@ def workload_config(args, scene, W, H, world):
         "levels": args.levels, "resolution": [W, H], "voxels": int(scene.n_voxels), "dag_words": int(scene.basic.size),
         "hash_pool_mib": round(scene.hash_pool.nbytes / 2**20, 1) if scene.has_hash else 0,
         "color_mib": round((scene.weights.nbytes + scene.blocks.nbytes + scene.macro_blocks.nbytes) / 2**20, 1),
-        "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, NCCL gather to rank 0",
+        "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, " + ("tiles stored into rank 0's frame over NVLink peer memory" if getattr(args, "exchange", "peer") == "peer" else "NCCL gather to rank 0"),
         "l2_policy": "inputs larger than L2: each step is a different camera pose over a DAG pool >> 126 MB",
         "shadow_bias": 1.0, "fog_density": 0.0,
         "beam_prefetch": not getattr(args, "no_beam_prefetch", False),
@@ -294,7 +296,31 @@ def run_ours(args):
             t_.set_stream(s_.cuda_stream)
         frame = frames[0] if rank == 0 else None
 
-        def gather(k):
+        if args.exchange == "peer":
+            # rank 0's frames are mapped into every rank (CUDA IPC); ranks store their tiles into them (csrc/hdt_exchange.cuh)
+            frames = []
+            for t_ in lanes:
+                box = [None]
+                if rank == 0:
+                    handle, fptr = t_.exchange_create()
+                    box = [handle]
+                    frames.append(torch.as_tensor(_Mem(fptr, W * H), device=dev))
+                else:
+                    frames.append(None)
+                dist.broadcast_object_list(box, src=0)
+                if rank != 0:
+                    t_.exchange_open(box[0])
+            frame = frames[0] if rank == 0 else None
+            dist.barrier()
+
+        def gather(k, release=True):
+            if os.environ.get("HDT_BENCH_NO_GATHER"):      # diagnostics only: how much of a step is the exchange
+                return
+            if args.exchange == "peer":
+                lanes[k].exchange_frame()
+                if rank == 0 and release:
+                    lanes[k].exchange_release()
+                return
             with torch.cuda.stream(streams[k]):
                 dist.gather(mine[k], list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
                 if rank == 0:
@@ -388,24 +414,30 @@ def run_ours(args):
     # context is synchronised (its host frame is complete and may be consumed) before it is given the next frame.
     for t_ in lanes:
         t_.set_option(tracer.OPT_BEAM_PREFETCH, 0)
-    host_frames = [host_frame] + [torch.empty(W * H, dtype=torch.int32).pin_memory() for _ in lanes[1:]] if rank == 0 and world == 1 else None
+    host_frames = [host_frame] + [torch.empty(W * H, dtype=torch.int32).pin_memory() for _ in lanes[1:]] if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         p = poses[(args.warmup + i) % len(poses)]
+        k = i % len(lanes)
         if world == 1:
-            k = i % len(lanes)
             if i >= len(lanes):
                 lanes[k].sync()
             lanes[k].enqueue_frame(camera.trace_params(p, info, args.levels, W, H), dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True,
                                    host_frames[k].data_ptr())
         else:
-            tr.resolve_frame(p, info, dag, colors, 1.0, 0.0, True, None)
-            gather(0)
+            # N > 1: the same two lanes as the device-timed loop.  Frame i (kernels -> NCCL gather -> assembly -> copy of the
+            # assembled frame into pinned host memory, all on stream k) overlaps frame i+1 on the other stream; a lane is
+            # synchronised -- its host frame complete -- before it is given the next frame.
+            if i >= len(lanes):
+                streams[k].synchronize()
+            lanes[k].enqueue_frame(camera.trace_params(p, info, args.levels, W, H), dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+            gather(k, release=False)
             if rank == 0:
-                with torch.cuda.stream(streams[0]):
-                    host_frame.copy_(frame, non_blocking=True)
-                streams[0].synchronize()
+                with torch.cuda.stream(streams[k]):
+                    host_frames[k].copy_(frames[k], non_blocking=True)
+                if args.exchange == "peer":
+                    lanes[k].exchange_release()          # after the copy on the same stream: the peers may overwrite frame k
     sync_all()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
@@ -426,6 +458,28 @@ def run_ours(args):
                 for k in range(3):
                     pass_ms[i][k] += ms[k] / reps
 
+    # ---- N > 1: the exchanged frame against the same frame rendered whole on rank 0 ----------
+    exchange_mismatch = None
+    if world > 1 and not os.environ.get("HDT_BENCH_NO_GATHER"):
+        exchange_mismatch = 0
+        whole = tracer.DAGTracer(True, W, H, args.levels, device=local_rank) if rank == 0 else None
+        for i in sample_ids[:2]:
+            lanes[0].enqueue_frame(params[i], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+            gather(0, release=False)
+            if rank == 0:
+                with torch.cuda.stream(streams[0]):
+                    host_frame.copy_(frames[0], non_blocking=True)
+                if args.exchange == "peer":
+                    lanes[0].exchange_release()
+            lanes[0].sync()
+            streams[0].synchronize()
+            if rank == 0:
+                whole.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
+                exchange_mismatch += int((whole.read_colors() != host_frame.numpy().view(np.uint32).reshape(H, W)).sum())
+        if whole is not None:
+            whole.close()
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -442,10 +496,12 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "setup_s": round(t_build, 1), "scene_build_s": round(scene.build_seconds, 1), "replication_bytes": int(replication_bytes),
-        "timing": ("cudaEvents on the tracer streams around K enqueued frames; two frames in flight, NCCL gather + assembly included, max over ranks" if gather
+        "timing": ("cudaEvents on the tracer streams around K enqueued frames; two frames in flight, " + ("tiles stored into rank 0's frame over peer memory (hdt_exchange_*)" if args.exchange == "peer" else "NCCL gather + assembly") + " included, max over ranks" if gather
                    else f"cudaEvents on the tracer streams around K enqueued frames, {len(lanes)} frame(s) in flight"),
         "wall_ms_per_step": wall_ms / args.steps,
     }
+    if exchange_mismatch is not None:
+        out["parity_check_mismatched_pixels_vs_whole_frame_on_rank0"] = exchange_mismatch
 
     # ---- CPU baseline + algorithmic bytes (bounded sample), roofline -------------------------
     if world == 1 and not args.no_cpu_baseline:

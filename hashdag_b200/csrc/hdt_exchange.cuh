@@ -1,0 +1,82 @@
+// Framebuffer exchange over peer memory (one process per GPU on an NVLink / NVSwitch box).
+//
+// Instead of an NCCL gather into a staging buffer followed by an assembly pass, the root's row-major frame is mapped
+// into every rank (CUDA IPC) and each rank stores the tiles it owns straight into it: the scatter kernel below writes
+// whole tile rows (256 B per 64-pixel row) through NVLink and its last CTA bumps an arrival counter in the root's
+// memory.  The root's stream waits for world-1 arrivals per frame (a one-thread kernel polling its own memory) and, once
+// the frame has been consumed, publishes a credit the peers wait for before overwriting the buffer.  No SM of the root
+// moves any pixel of the other ranks, and nothing synchronises with the host.
+//
+//   exchange block (root's device memory):  [ frame u32[W*H] | pad | arrivals u32 | credit u32 ]
+//   lane sequence numbers start at 1:  arrivals target = (world-1) * seq,  credit published = seq,  peers wait credit >= seq-1
+#pragma once
+#include "hdt_device.cuh"
+
+namespace hdt {
+
+struct ExchangeCounters { u32 arrivals; u32 credit; u32 pad[62]; };   // 256 B, lives behind the frame
+
+__device__ __forceinline__ u32 load_volatile(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
+
+// One thread: wait until *counter - target >= 0 (wrap-safe).  Gives up after ~2 s of GPU time and raises *timedOut
+// (host-mapped), so a lost peer shows up as an error instead of a hung box.
+__global__ void exchange_wait_kernel(const u32* counter, u32 target, u32* timedOut)
+{
+    const long long t0 = clock64();
+    while (int(load_volatile(counter) - target) < 0) {
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000ll) { *reinterpret_cast<volatile u32*>(timedOut) = 1; break; }
+    }
+    __threadfence_system();
+}
+
+__global__ void exchange_publish_kernel(u32* counter, u32 value)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile u32*>(counter) = value;
+}
+
+__global__ void exchange_signal_kernel(u32* arrivals)   // a rank that owns no tile still has to arrive
+{
+    __threadfence_system();
+    atomicAdd_system(arrivals, 1u);
+}
+
+// This rank's compact tiles (each (1<<tileLog2)^2 pixels, row-major, owned tiles back to back) -> the row-major frame,
+// which may live in another GPU's memory.  One CTA per 16 tile rows; the last CTA to finish signals `arrivals`.
+__global__ void __launch_bounds__(256) exchange_scatter_kernel(const u32* __restrict__ compact, u32* __restrict__ frame, const PixelMap map,
+                                                                u32* __restrict__ ctasDone, u32* arrivals)
+{
+    const u32 T = 1u << map.tileLog2, rowsPerCta = 16, ctasPerTile = T / rowsPerCta;
+    const u32 slot = blockIdx.x / ctasPerTile, row0 = (blockIdx.x % ctasPerTile) * rowsPerCta;
+    const u32 t = map.rank + slot * map.world;
+    const u32 x0 = (t % map.tilesX) * T, y0 = (t / map.tilesX) * T;
+    const u32* src = compact + (u64(slot) << (2 * map.tileLog2));
+    if ((map.width & 3) == 0) {
+        const u32 vecPerRow = T / 4;
+        for (u32 i = threadIdx.x; i < rowsPerCta * vecPerRow; i += blockDim.x) {
+            const u32 r = row0 + i / vecPerRow, c = (i % vecPerRow) * 4;
+            const u32 x = x0 + c, y = y0 + r;
+            if (y < map.height && x < map.width)      // width % 4 == 0: a vector is inside or outside as a whole
+                *reinterpret_cast<uint4*>(frame + u64(y) * map.width + x) = *reinterpret_cast<const uint4*>(src + r * T + c);
+        }
+    } else {
+        for (u32 i = threadIdx.x; i < rowsPerCta * T; i += blockDim.x) {
+            const u32 r = row0 + i / T, c = i % T;
+            const u32 x = x0 + c, y = y0 + r;
+            if (y < map.height && x < map.width) frame[u64(y) * map.width + x] = src[r * T + c];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u32 prev = atomicAdd(ctasDone, 1u);
+        if (prev == gridDim.x - 1) {
+            *ctasDone = 0;                            // ready for the next launch (stream order separates launches)
+            __threadfence_system();
+            if (arrivals) atomicAdd_system(arrivals, 1u);
+        }
+    }
+}
+
+}  // namespace hdt

@@ -14,6 +14,7 @@
 #include "hdt_color_leaf.cuh"
 #include "hdt_colors.cuh"
 #include "hdt_device.cuh"
+#include "hdt_exchange.cuh"
 #include "hdt_region.cuh"
 
 using namespace hdt;
@@ -421,6 +422,12 @@ struct hdt_ctx {
     u32 beamMaxVisits = 32;
     u32 beamTag = 0;                    // bumped per beam launch; per-ray kernels ignore states of other launches
     int lastBeamPass = 0;
+    // framebuffer exchange over peer memory (hdt_exchange.cuh)
+    u32* xBlock = nullptr;              // [frame W*H][ExchangeCounters]: own allocation (root) or a mapping of the root's
+    bool xOwned = false, xIpc = false;
+    u32 xSeq = 0;                       // frames exchanged on this context
+    u32* xCtasDone = nullptr;           // device, scatter kernel's last-CTA counter
+    u32* xTimedOut = nullptr;           // pinned + mapped: raised by a wait kernel that gave up
     char* stagingHost = nullptr;        // hdt_apply_ranges_host: pinned + device staging, bump-allocated, reset when full
     char* stagingDev = nullptr;
     size_t stagingCap = 0, stagingUsed = 0;
@@ -748,6 +755,10 @@ int hdt_destroy(hdt_ctx* c)
     for (auto& e : c->timer) if (e) cudaEventDestroy(e);
     cudaFree(c->hitCounter);
     cudaFree(c->tables);
+    if (c->xBlock && c->xOwned) cudaFree(c->xBlock);
+    if (c->xBlock && c->xIpc) cudaIpcCloseMemHandle(c->xBlock);
+    cudaFree(c->xCtasDone);
+    if (c->xTimedOut) cudaFreeHost(c->xTimedOut);
     cudaFree(c->rebuildScratch);
     if (c->stagingHost) cudaFreeHost(c->stagingHost);
     cudaFree(c->stagingDev);
@@ -885,6 +896,10 @@ int hdt_sync(hdt_ctx* c)
     HDT_CUDA(cudaSetDevice(c->device));
     HDT_CUDA(cudaStreamSynchronize(c->stream));
     HDT_CUDA(cudaGetLastError());
+    if (c->xTimedOut && *reinterpret_cast<volatile u32*>(c->xTimedOut)) {
+        *reinterpret_cast<volatile u32*>(c->xTimedOut) = 0;
+        return fail(HDT_ERR_STATE, "framebuffer exchange: a rank did not arrive (or rank 0 did not release) within ~2 s of GPU time");
+    }
     return HDT_OK;
 }
 
@@ -1055,6 +1070,121 @@ int hdt_apply_ranges(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload_dev,
     apply_ranges_kernel<<<n_ranges < 1184 ? n_ranges : 1184, 128, 0, c->stream>>>(dst_dev, payload_dev, ranges_dev, n_ranges);
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+// ---- framebuffer exchange over peer memory (hdt_exchange.cuh) ---------------------------------------
+namespace {
+size_t exchange_frame_bytes(const hdt_ctx* c) { return (size_t(c->map.width) * c->map.height * 4 + 255) & ~size_t(255); }
+ExchangeCounters* exchange_counters(const hdt_ctx* c) { return reinterpret_cast<ExchangeCounters*>(reinterpret_cast<char*>(c->xBlock) + exchange_frame_bytes(c)); }
+int exchange_common(hdt_ctx* c)
+{
+    if (!c->xCtasDone) {
+        HDT_CUDA(cudaMalloc(&c->xCtasDone, sizeof(u32)));
+        HDT_CUDA(cudaMemset(c->xCtasDone, 0, sizeof(u32)));
+    }
+    if (!c->xTimedOut) {
+        HDT_CUDA(cudaHostAlloc(&c->xTimedOut, sizeof(u32), cudaHostAllocMapped));
+        *c->xTimedOut = 0;
+    }
+    c->xSeq = 0;
+    return HDT_OK;
+}
+}  // namespace
+
+int hdt_exchange_create(hdt_ctx* c, uint8_t ipc_handle_out[HDT_IPC_HANDLE_BYTES], void** frame_dev_out)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    if (c->map.rank != 0) return fail(HDT_ERR_STATE, "hdt_exchange_create: only rank 0 owns the frame");
+    if (c->xBlock) return fail(HDT_ERR_STATE, "hdt_exchange_create: the context already has an exchange");
+    static_assert(sizeof(cudaIpcMemHandle_t) == HDT_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    HDT_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = exchange_frame_bytes(c) + sizeof(ExchangeCounters);
+    HDT_CUDA(cudaMalloc(&c->xBlock, bytes));
+    HDT_CUDA(cudaMemset(c->xBlock, 0, bytes));
+    c->xOwned = true;
+    if (int rc = exchange_common(c)) return rc;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        HDT_CUDA(cudaIpcGetMemHandle(&h, c->xBlock));
+        memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    if (frame_dev_out) *frame_dev_out = c->xBlock;
+    return HDT_OK;
+}
+
+int hdt_exchange_open(hdt_ctx* c, const uint8_t ipc_handle[HDT_IPC_HANDLE_BYTES])
+{
+    if (!c || !ipc_handle) return fail(HDT_ERR_ARG, "null argument");
+    if (c->map.rank == 0) return fail(HDT_ERR_STATE, "hdt_exchange_open: rank 0 creates the exchange");
+    if (c->xBlock) return fail(HDT_ERR_STATE, "hdt_exchange_open: the context already has an exchange");
+    HDT_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    void* p = nullptr;
+    HDT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->xBlock = static_cast<u32*>(p);
+    c->xIpc = true;
+    return exchange_common(c);
+}
+
+int hdt_exchange_block(hdt_ctx* c, void** block_dev_out)
+{
+    if (!c || !block_dev_out) return fail(HDT_ERR_ARG, "null argument");
+    if (!c->xBlock) return fail(HDT_ERR_STATE, "no exchange on this context");
+    *block_dev_out = c->xBlock;
+    return HDT_OK;
+}
+
+int hdt_exchange_attach(hdt_ctx* c, void* block_dev)
+{
+    if (!c || !block_dev) return fail(HDT_ERR_ARG, "null argument");
+    if (c->map.rank == 0) return fail(HDT_ERR_STATE, "hdt_exchange_attach: rank 0 creates the exchange");
+    if (c->xBlock) return fail(HDT_ERR_STATE, "hdt_exchange_attach: the context already has an exchange");
+    HDT_CUDA(cudaSetDevice(c->device));
+    c->xBlock = static_cast<u32*>(block_dev);
+    return exchange_common(c);
+}
+
+int hdt_exchange_frame(hdt_ctx* c)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    if (!c->xBlock) return fail(HDT_ERR_STATE, "hdt_exchange_frame: no exchange (hdt_exchange_create / open / attach first)");
+    HDT_CUDA(cudaSetDevice(c->device));
+    const u32 seq = ++c->xSeq;
+    ExchangeCounters* k = exchange_counters(c);
+    u32* timedOutDev = nullptr;
+    HDT_CUDA(cudaHostGetDevicePointer(&timedOutDev, c->xTimedOut, 0));
+    const u32 T = 1u << c->map.tileLog2;
+    const u32 grid = c->nOwnedTiles * (T / 16);
+    const bool root = c->map.rank == 0;
+    if (!root) {   // the root must have consumed the previous frame of this lane before it is overwritten
+        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, timedOutDev);
+        ++c->launches;
+    }
+    if (grid) {
+        exchange_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->colors, c->xBlock, c->map, c->xCtasDone, root ? nullptr : &k->arrivals);
+        ++c->launches;
+    } else if (!root) {
+        exchange_signal_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals);
+        ++c->launches;
+    }
+    if (root && c->map.world > 1) {
+        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals, (c->map.world - 1) * seq, timedOutDev);
+        ++c->launches;
+    }
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
+int hdt_exchange_release(hdt_ctx* c)
+{
+    if (!c) return fail(HDT_ERR_ARG, "null context");
+    if (!c->xBlock || c->map.rank != 0) return fail(HDT_ERR_STATE, "hdt_exchange_release: rank 0 with an exchange only");
+    HDT_CUDA(cudaSetDevice(c->device));
+    exchange_publish_kernel<<<1, 1, 0, c->stream>>>(&exchange_counters(c)->credit, c->xSeq);
+    ++c->launches;
     HDT_CUDA(cudaGetLastError());
     return HDT_OK;
 }

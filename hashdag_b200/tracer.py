@@ -35,7 +35,8 @@ EXPORTS = (
     "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_set_option", "hdt_beam_stats", "hdt_pass_timeline", "hdt_resolve_paths", "hdt_resolve_colors",
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
-    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_version",
+    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_exchange_create", "hdt_exchange_open", "hdt_exchange_block", "hdt_exchange_attach",
+    "hdt_exchange_frame", "hdt_exchange_release", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_version",
 )
 ERR_CAPACITY = 4
 
@@ -85,6 +86,12 @@ def load_library():
     lib.hdt_read_colors.argtypes = [C.c_void_p, C.c_void_p]
     lib.hdt_partition_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.hdt_assemble_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hdt_exchange_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.hdt_exchange_open.argtypes = [C.c_void_p, C.c_char_p]
+    lib.hdt_exchange_block.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.hdt_exchange_attach.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hdt_exchange_frame.argtypes = [C.c_void_p]
+    lib.hdt_exchange_release.argtypes = [C.c_void_p]
     lib.hdt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.hdt_apply_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.hdt_apply_ranges_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
@@ -372,6 +379,35 @@ class DAGTracer:
 
     def assemble_colors(self, gathered_tensor, frame_tensor=None):
         _check(self._lib.hdt_assemble_colors(self._ctx, gathered_tensor.data_ptr(), 0 if frame_tensor is None else frame_tensor.data_ptr()))
+
+    # -- framebuffer exchange over peer memory (csrc/hdt_exchange.cuh) ---------------------------
+    def exchange_create(self):
+        """Rank 0: allocate the shared row-major frame -> (64-byte CUDA IPC handle for the other processes, frame device pointer)."""
+        h = C.create_string_buffer(64)
+        p = C.c_void_p()
+        _check(self._lib.hdt_exchange_create(self._ctx, h, C.byref(p)))
+        return h.raw, p.value
+
+    def exchange_open(self, ipc_handle: bytes):
+        """Other ranks (other processes): map rank 0's frame."""
+        _check(self._lib.hdt_exchange_open(self._ctx, C.create_string_buffer(ipc_handle, 64)))
+
+    def exchange_block(self) -> int:
+        p = C.c_void_p()
+        _check(self._lib.hdt_exchange_block(self._ctx, C.byref(p)))
+        return p.value
+
+    def exchange_attach(self, block_ptr: int):
+        """Other ranks living in rank 0's process: attach by pointer (CUDA IPC cannot open a handle in its own process)."""
+        _check(self._lib.hdt_exchange_attach(self._ctx, block_ptr))
+
+    def exchange_frame(self):
+        """Every rank, after the frame's passes: store the owned tiles into rank 0's frame (asynchronous)."""
+        _check(self._lib.hdt_exchange_frame(self._ctx))
+
+    def exchange_release(self):
+        """Rank 0, once the work that reads the frame is queued: let the other ranks overwrite it."""
+        _check(self._lib.hdt_exchange_release(self._ctx))
 
     def apply_ranges(self, dst_tensor, payload_tensor, ranges_tensor, n_ranges: int):
         """dst[r.dst_word + i] = payload[r.src_word + i] for every hdt_range r (edit-dirtied spans, see edits.py)."""

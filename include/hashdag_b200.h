@@ -179,6 +179,24 @@ int hdt_partition_buffers(hdt_ctx* ctx, void** paths_dev, void** colors_dev, uin
 /* Rank 0: scatter `world` gathered compact colour buffers (each max_tiles_per_rank tiles) into the row-major frame.
  * Asynchronous: enqueued on the tracer's stream, complete after hdt_sync(). */
 int hdt_assemble_colors(hdt_ctx* ctx, const uint32_t* gathered_dev, uint32_t* frame_dev_or_null);
+/* Framebuffer exchange over peer memory (NVLink), the alternative to gather + hdt_assemble_colors: rank 0's row-major
+ * colour frame is mapped into every rank and each rank stores its own tiles straight into it (csrc/hdt_exchange.cuh).
+ * Call after hdt_set_partition.  Rank 0: hdt_exchange_create allocates the frame (+ two counters behind it) and returns
+ * its CUDA IPC handle (64 bytes) for the other processes, which call hdt_exchange_open; contexts of the SAME process
+ * attach by pointer instead (hdt_exchange_block of the root -> hdt_exchange_attach).
+ * Per frame, every rank calls hdt_exchange_frame after its passes (asynchronous, tracer's stream): other ranks wait for
+ * rank 0's credit, scatter their tiles and signal; rank 0 scatters its own tiles and waits for world-1 arrivals, after
+ * which work queued on its stream may read the frame.  Rank 0 calls hdt_exchange_release once that work is queued; it
+ * publishes the credit that lets the others overwrite the frame.  A peer that never arrives makes the wait give up after
+ * ~2 s of GPU time: hdt_sync() then returns HDT_ERR_STATE. */
+#define HDT_IPC_HANDLE_BYTES 64
+int hdt_exchange_create(hdt_ctx* ctx, uint8_t ipc_handle_out[HDT_IPC_HANDLE_BYTES], void** frame_dev_out);
+int hdt_exchange_open(hdt_ctx* ctx, const uint8_t ipc_handle[HDT_IPC_HANDLE_BYTES]);
+int hdt_exchange_block(hdt_ctx* ctx, void** block_dev_out);
+int hdt_exchange_attach(hdt_ctx* ctx, void* block_dev);
+int hdt_exchange_frame(hdt_ctx* ctx);
+int hdt_exchange_release(hdt_ctx* ctx);
+
 /* Run the tracer on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL = back to the
  * context's own stream), so that frames, the NCCL gather and the assembly queue up on one stream
  * without host synchronisation in between. */

@@ -205,6 +205,62 @@ def test_partitioned_render_assembles_to_the_whole_frame(tr):
     t0.close()
 
 
+class _DevMem:
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def test_peer_exchange_assembles_the_whole_frame(tr):
+    """hdt_exchange_*: three ranks (contexts of this process, attached by pointer) store their tiles straight into rank
+    0's frame; arrivals / credit counters order the frames.  Three frames in a row == the unpartitioned frames."""
+    import torch
+    from hashdag_b200 import tracer
+    s = get_scene(13, 10)
+    cams = scene_cameras(s, 3, 10)[:3]
+    dag, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
+    whole = tr(13)
+    world, tl = 3, 5
+    ranks = []
+    for r in range(world):
+        t = tracer.DAGTracer(True, W, H, 13)
+        t.set_partition(r, world, tl)
+        ranks.append(t)
+    _, frame_ptr = ranks[0].exchange_create()
+    for t in ranks[1:]:
+        t.exchange_attach(ranks[0].exchange_block())
+    frame = torch.as_tensor(_DevMem(frame_ptr, W * H), device="cuda")
+    info = _info(s)
+    for cam in cams:
+        whole.resolve_frame(cam, info, dag, col, 1.0, 0.0, True)
+        want = whole.read_colors()
+        prm = camera.trace_params(cam, info, 13, W, H)
+        for t in ranks[1:] + ranks[:1]:          # the root last: its wait needs the peers' work queued (one host thread here)
+            t.enqueue_frame(prm, dag.pod(), dag.kind, col.pod(), col.kind, 1.0, 0.0, True, None)
+            t.exchange_frame()
+        ranks[0].sync()
+        got = frame.cpu().numpy().view(np.uint32).reshape(H, W)
+        assert np.array_equal(got, want)
+        frame.zero_()
+        torch.cuda.synchronize()
+        ranks[0].exchange_release()
+    for t in ranks:
+        t.sync()
+        t.close()
+
+
+def test_peer_exchange_gives_up_on_a_missing_rank():
+    from hashdag_b200 import tracer
+    s = get_scene(13, 10)
+    t = tracer.DAGTracer(True, W, H, 13)
+    t.set_partition(0, 2, 5)
+    t.exchange_create()
+    t.exchange_frame()                            # rank 1 never arrives
+    with pytest.raises(tracer.TracerError):
+        t.sync()
+    t.sync()                                      # the error is reported once
+    t.close()
+
+
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
 
 
