@@ -143,7 +143,7 @@ def test_hashdag_layout_rules():
         assert ptr % 2 == 0
 
 
-GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_d[0-9]*.npz")))
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
