@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dag", default="hash", choices=["hash", "basic"])
     ap.add_argument("--no-beam-prefetch", action="store_true", help="keep the beam kernels of frame n+1 behind all of frame n")
+    ap.add_argument("--no-resolved", action="store_true", help="trace the HashDAG through its page table (A/B); default: the resolved pool (hdt_hash_dag_resolve)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the tiles reach rank 0's frame -- stores over peer memory (hdt_exchange_*, default) or NCCL gather + assembly (A/B)")
     ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
@@ -169,6 +170,7 @@ def workload_config(args, scene, W, H, world):
         "l2_policy": "inputs larger than L2: each step is a different camera pose over a DAG pool >> 126 MB",
         "shadow_bias": 1.0, "fog_density": 0.0,
         "beam_prefetch": not getattr(args, "no_beam_prefetch", False),
+        "hash_dag_pointers": "resolved pool (child pointers pre-translated once, hdt_hash_dag_resolve)" if (getattr(args, "dag", "hash") == "hash" and not getattr(args, "no_resolved", False)) else "as stored",
         "frames_in_flight": 2 if world > 1 else getattr(args, "frames_in_flight", 1),
     }
 
@@ -270,6 +272,11 @@ def run_ours(args):
     if world > 1:
         tr.set_partition(rank, world, tile_log2)
     params = [camera.trace_params(p, info, args.levels, W, H) for p in poses]
+    if hashed and not args.no_resolved:
+        # the HashDAG's child pointers pushed through the page table once, into a second pool (csrc/hdt_resolve.cuh)
+        torch.cuda.synchronize()
+        dag = tr.resolve_hash_dag(dag)
+        tr.sync()
     dag_pod, col_pod = dag.pod(), colors.pod()
 
     # ---- multi-GPU gather plumbing ----------------------------------------------------------
@@ -457,6 +464,19 @@ def run_ours(args):
                 ms = tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
                 for k in range(3):
                     pass_ms[i][k] += ms[k] / reps
+    elif not args.no_cpu_baseline:
+        # N > 1: each rank times its own (1/N of the tiles) passes on two sample poses; the slowest rank counts
+        sample_ids = sample_ids[:2]
+        pass_ms = {i: [0.0, 0.0, 0.0] for i in sample_ids}
+        for _ in range(3):
+            for i in sample_ids:
+                ms = tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
+                for k in range(3):
+                    pass_ms[i][k] += ms[k] / 3
+        pt = torch.tensor([pass_ms[i] for i in sample_ids], dtype=torch.float64, device=dev)
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        for row, i in zip(pt.tolist(), sample_ids):
+            pass_ms[i] = row
 
     # ---- N > 1: the exchanged frame against the same frame rendered whole on rank 0 ----------
     exchange_mismatch = None
@@ -546,6 +566,31 @@ def run_ours(args):
                            "avg_launch_ms": gpu_ms_pass[dominant] / len(sample_ids),
                            "per_pass": {k: {"ms": gpu_ms_pass[k] / len(sample_ids), "algorithmic_GBps": ach[k],
                                             "bytes_per_launch": bytes_pass[k] / len(sample_ids)} for k in bytes_pass}}
+    if world > 1 and not args.no_cpu_baseline:
+        # roofline of one rank's launch: the frame's algorithmic bytes (oracle access counts on rank 0's host cores) / N,
+        # over the slowest rank's pass time
+        from oracle import hdo
+        odag = hdo.make_dag(scene, hdo.DAG_HASH if hashed else hdo.DAG_BASIC)
+        ocol = hdo.make_colors(scene, hdo.COLORS_HASH if hashed else hdo.COLORS_COMPRESSED)
+        bytes_pass = {"paths": 0, "colors": 0, "shadows": 0}
+        gpu_ms_pass = {"paths": 0.0, "colors": 0.0, "shadows": 0.0}
+        for i in sample_ids:
+            _, _, (sp, sc, ss), _ = oracle_frame(hdo, odag, ocol, params[i], W, H)
+            b = algorithmic_bytes(sp, sc, ss, hashed, W, H)
+            for k, name in enumerate(("paths", "colors", "shadows")):
+                bytes_pass[name] += b[name] / world
+                gpu_ms_pass[name] += pass_ms[i][k]
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        dominant = max(gpu_ms_pass, key=lambda k: gpu_ms_pass[k])
+        ach = {k: (bytes_pass[k] / (gpu_ms_pass[k] * 1e-3) / 1e9 if gpu_ms_pass[k] > 0 else 0.0) for k in bytes_pass}
+        out["roofline"] = {"bound": "hbm", "kernel": f"{dominant} pass of ONE rank (1/{world} of the tiles) = setup_{dominant}_kernel + beam_{dominant}_kernel + trace_{dominant}_kernel" if dominant != "colors" else "trace_colors_kernel of one rank",
+                           "achieved": ach[dominant], "peak": peak, "unit": "GB/s", "frac": ach[dominant] / peak, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": bytes_pass[dominant] / len(sample_ids), "avg_launch_ms": gpu_ms_pass[dominant] / len(sample_ids),
+                           "note": f"per-GPU figure: the frame's algorithmic bytes / {world} over the slowest rank's synchronous pass time, {len(sample_ids)} sample poses"}
     print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -66,6 +66,25 @@ struct HashDagDev {
     __device__ __forceinline__ uint2 leaf(u32 h) const { return __ldg(reinterpret_cast<const uint2*>(pool + h)); }
 };
 
+// A HashDAG whose child words have been pushed through the page table ONCE (hdt_hash_dag_resolve, hdt_resolve.cuh):
+// `pool` is a library-format copy of the caller's pool with the same physical layout in which every child pointer
+// holds the physical word index of the child.  A descent is then two dependent loads (child word, child header) like
+// BasicDAG's instead of three.  The caller's pool and page table stay at hand for the two debug views that display the
+// reference's virtual indices.
+struct HashDagResolvedDev {
+    const u32* __restrict__ pool;        // resolved copy
+    const u32* __restrict__ vpool;       // the caller's pool (virtual child pointers)
+    const u32* __restrict__ pageTable;
+    u32 firstNodeIndex;
+    __device__ __forceinline__ u32 to_handle(u32 vptr) const { return __ldg(pageTable + (vptr >> 9)) * kPageWords + (vptr & (kPageWords - 1)); }
+    __device__ __forceinline__ u32 root() const { return to_handle(firstNodeIndex); }
+    __device__ __forceinline__ u32 raw_root() const { return firstNodeIndex; }
+    __device__ __forceinline__ u32 header(u32 h) const { return __ldg(pool + h); }
+    __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(vpool + h + off); }
+    __device__ __forceinline__ u32 child(u32 h, u32 off) const { return __ldg(pool + h + off); }
+    __device__ __forceinline__ uint2 leaf(u32 h) const { return __ldg(reinterpret_cast<const uint2*>(pool + h)); }
+};
+
 // base_dag.h:16-58
 __device__ __forceinline__ u32 first_child_mask(uint2 leaf)
 {

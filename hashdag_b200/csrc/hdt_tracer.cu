@@ -16,11 +16,13 @@
 #include "hdt_device.cuh"
 #include "hdt_exchange.cuh"
 #include "hdt_region.cuh"
+#include "hdt_resolve.cuh"
 
 using namespace hdt;
 
 static_assert(sizeof(hdt_basic_dag) == 16, "BasicDAG layout");
 static_assert(sizeof(hdt_hash_dag) == 32, "HashDAG layout");
+static_assert(sizeof(hdt_resolved_hash_dag) == 40, "hdt_resolved_hash_dag layout");
 static_assert(sizeof(hdt_color_leaf) == 104, "CompressedColorLeaf layout");
 static_assert(sizeof(hdt_basic_compressed_colors) == 128, "BasicDAGCompressedColors layout");
 static_assert(sizeof(hdt_basic_uncompressed_colors) == 40, "BasicDAGUncompressedColors layout");
@@ -437,6 +439,8 @@ struct hdt_ctx {
     char* stagingHost = nullptr;        // hdt_apply_ranges_host: pinned + device staging, bump-allocated, reset when full
     char* stagingDev = nullptr;
     size_t stagingCap = 0, stagingUsed = 0;
+    u32* physToVirt = nullptr;          // hdt_hash_dag_resolve: physical page -> virtual page (grow-only)
+    size_t physToVirtPages = 0;
     void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, per-macro-block sums (grow-only)
     size_t rebuildScratchBytes = 0;
 
@@ -490,7 +494,7 @@ int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
     return HDT_OK;
 }
 
-struct DagArg { int kind; BasicDagDev basic; HashDagDev hash; };
+struct DagArg { int kind; BasicDagDev basic; HashDagDev hash; HashDagResolvedDev resolved; };
 
 int parse_dag(int kind, const void* pod, size_t size, DagArg& out)
 {
@@ -509,6 +513,16 @@ int parse_dag(int kind, const void* pod, size_t size, DagArg& out)
         if (!d.pool || !d.page_table) return fail(HDT_ERR_ARG, "HashDAG: null pool / page table");
         if (u64(d.pool_top) * kPageWords > (u64(1) << 32)) return fail(HDT_ERR_ARG, "HashDAG: pool beyond 2^32 words");
         out.hash.pool = d.pool; out.hash.pageTable = d.page_table; out.hash.firstNodeIndex = d.first_node_index;
+        return HDT_OK;
+    }
+    if (kind == HDT_DAG_HASH_RESOLVED) {
+        if (size != sizeof(hdt_resolved_hash_dag)) return fail(HDT_ERR_POD_SIZE, "hdt_resolved_hash_dag: expected 40 bytes");
+        hdt_resolved_hash_dag d; memcpy(&d, pod, sizeof(d));
+        if (!d.dag.pool || !d.dag.page_table || !d.resolved_pool) return fail(HDT_ERR_ARG, "resolved HashDAG: null pool / page table / resolved pool");
+        if (u64(d.dag.pool_top) * kPageWords > (u64(1) << 32)) return fail(HDT_ERR_ARG, "HashDAG: pool beyond 2^32 words");
+        if ((d.dag.first_node_index >> 9) >= d.dag.page_table_size) return fail(HDT_ERR_ARG, "resolved HashDAG: root outside the page table");
+        out.resolved.pool = d.resolved_pool; out.resolved.vpool = d.dag.pool; out.resolved.pageTable = d.dag.page_table;
+        out.resolved.firstNodeIndex = d.dag.first_node_index;
         return HDT_OK;
     }
     return fail(HDT_ERR_ARG, "unknown DAG kind");
@@ -619,14 +633,16 @@ void launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
         const u32 nb = c->n_beams();
         const dim3 g((nb + 31) / 32), b(32);
         if (d.kind == HDT_DAG_BASIC) beam_paths_kernel<BasicDagDev><<<g, b, 0, c->side>>>(cam, d.basic, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
-        else beam_paths_kernel<HashDagDev><<<g, b, 0, c->side>>>(cam, d.hash, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
+        else if (d.kind == HDT_DAG_HASH) beam_paths_kernel<HashDagDev><<<g, b, 0, c->side>>>(cam, d.hash, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
+        else beam_paths_kernel<HashDagResolvedDev><<<g, b, 0, c->side>>>(cam, d.resolved, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
         ++c->launches;
         c->lastBeamPass = 0;
     }
     cudaEventRecord(c->join[0], c->side);
     cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[0] : c->setupDone[0], 0);   // the directions
     if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
-    else trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
+    else if (d.kind == HDT_DAG_HASH) trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
+    else trace_paths_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, d.resolved, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
     cudaEventRecord(c->traceDone[0], c->stream);
     ++c->launches;
     cudaStreamWaitEvent(c->stream, c->join[0], 0);   // a synchronisation of the main stream covers the beam kernel too
@@ -636,7 +652,8 @@ void launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const Colo
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     if (!grid.x) return;
     if (d.kind == HDT_DAG_BASIC) trace_colors_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(d.basic, col, c->levels, prm, c->map, c->paths, c->colors);
-    else trace_colors_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(d.hash, col, c->levels, prm, c->map, c->paths, c->colors);
+    else if (d.kind == HDT_DAG_HASH) trace_colors_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(d.hash, col, c->levels, prm, c->map, c->paths, c->colors);
+    else trace_colors_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(d.resolved, col, c->levels, prm, c->map, c->paths, c->colors);
     ++c->launches;
 }
 // trace_shadows in two halves so that a whole-frame call can enqueue the first one (ray setup + beams, which
@@ -660,7 +677,8 @@ ShadowPrep prepare_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam,
         const u32 nb = c->n_beams();
         const dim3 g((nb + 31) / 32), b(32);
         if (d.kind == HDT_DAG_BASIC) beam_shadows_kernel<BasicDagDev><<<g, b, 0, c->side>>>(sp, d.basic, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
-        else beam_shadows_kernel<HashDagDev><<<g, b, 0, c->side>>>(sp, d.hash, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
+        else if (d.kind == HDT_DAG_HASH) beam_shadows_kernel<HashDagDev><<<g, b, 0, c->side>>>(sp, d.hash, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
+        else beam_shadows_kernel<HashDagResolvedDev><<<g, b, 0, c->side>>>(sp, d.resolved, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
         ++c->launches;
         c->lastBeamPass = 1;
     }
@@ -673,7 +691,8 @@ void finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const 
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[1] : c->setupDone[1], 0);   // the origins
     if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
-    else trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
+    else if (d.kind == HDT_DAG_HASH) trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
+    else trace_shadows_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, sp, d.resolved, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
     cudaEventRecord(c->traceDone[1], c->stream);
     ++c->launches;
     cudaStreamWaitEvent(c->stream, c->join[1], 0);
@@ -686,7 +705,7 @@ void launch_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const 
 int check_combo(int dagKind, int colorsKind)
 {
     // the instantiations the reference provides (tracer.cu:705-711)
-    if ((dagKind == HDT_DAG_HASH) != (colorsKind == HDT_COLORS_HASH)) return fail(HDT_ERR_ARG, "DAG / colours combination not provided by the tracer");
+    if ((dagKind == HDT_DAG_HASH || dagKind == HDT_DAG_HASH_RESOLVED) != (colorsKind == HDT_COLORS_HASH)) return fail(HDT_ERR_ARG, "DAG / colours combination not provided by the tracer");
     return HDT_OK;
 }
 
@@ -765,6 +784,7 @@ int hdt_destroy(hdt_ctx* c)
     if (c->xBlock && c->xIpc) cudaIpcCloseMemHandle(c->xBlock);
     cudaFree(c->xCtasDone);
     if (c->xTimedOut) cudaFreeHost(c->xTimedOut);
+    cudaFree(c->physToVirt);
     cudaFree(c->rebuildScratch);
     if (c->stagingHost) cudaFreeHost(c->stagingHost);
     cudaFree(c->stagingDev);
@@ -1231,6 +1251,70 @@ int hdt_apply_ranges_host(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload
     return HDT_OK;
 }
 
+int hdt_hash_dag_resolve(hdt_ctx* c, const hdt_hash_dag* dag, size_t dag_size, uint32_t* resolved_pool_dev, uint64_t capacity_words,
+                         const hdt_range* ranges_host, uint32_t n_ranges)
+{
+    if (!c || !dag || !resolved_pool_dev) return fail(HDT_ERR_ARG, "hdt_hash_dag_resolve: null argument");
+    if (dag_size != sizeof(hdt_hash_dag)) return fail(HDT_ERR_POD_SIZE, "HashDAG: expected 32 bytes");
+    if (!dag->pool || !dag->page_table) return fail(HDT_ERR_ARG, "HashDAG: null pool / page table");
+    const u64 poolWords = u64(dag->pool_top) * kPageWords;
+    if (poolWords > (u64(1) << 32)) return fail(HDT_ERR_ARG, "HashDAG: pool beyond 2^32 words");
+    if (capacity_words < poolWords) return fail(HDT_ERR_CAPACITY, "hdt_hash_dag_resolve: resolved pool smaller than pool_top pages");
+    if (!ranges_host && n_ranges) return fail(HDT_ERR_ARG, "hdt_hash_dag_resolve: null ranges");
+    if (!dag->pool_top) return HDT_OK;
+    // pages to refresh: all of them, or those the spans touch
+    std::vector<u32> pages;
+    if (ranges_host) {
+        for (u32 i = 0; i < n_ranges; ++i) {
+            const hdt_range& r = ranges_host[i];
+            if (!r.n_words) continue;
+            if (r.dst_word + r.n_words > poolWords) return fail(HDT_ERR_ARG, "hdt_hash_dag_resolve: a range lies beyond pool_top");
+            for (u64 p = r.dst_word / kPageWords; p <= (r.dst_word + r.n_words - 1) / kPageWords; ++p)
+                if (pages.empty() || pages.back() != u32(p)) pages.push_back(u32(p));
+        }
+        if (pages.empty()) return HDT_OK;
+    }
+    HDT_CUDA(cudaSetDevice(c->device));
+    if (c->physToVirtPages < dag->pool_top) {
+        HDT_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->physToVirt); c->physToVirt = nullptr; c->physToVirtPages = 0;
+        const size_t n = size_t(dag->pool_top) + size_t(dag->pool_top) / 4 + 1024;
+        HDT_CUDA(cudaMalloc(&c->physToVirt, n * sizeof(u32)));
+        c->physToVirtPages = n;
+    }
+    HDT_CUDA(cudaMemsetAsync(c->physToVirt, 0xFF, size_t(dag->pool_top) * sizeof(u32), c->stream));
+    map_pages_kernel<<<(dag->page_table_size + 255) / 256, 256, 0, c->stream>>>(dag->page_table, dag->page_table_size, c->physToVirt, dag->pool_top);
+    ++c->launches;
+    const u32* dPages = nullptr;
+    u32 nPages = dag->pool_top;
+    if (ranges_host) {
+        // the page list travels through the same pinned staging as hdt_apply_ranges_host
+        const size_t need = (pages.size() * sizeof(u32) + 255) & ~size_t(255);
+        if (c->stagingUsed + need > c->stagingCap) {
+            HDT_CUDA(cudaStreamSynchronize(c->stream));
+            c->stagingUsed = 0;
+            if (need > c->stagingCap) {
+                const size_t cap = need * 2 > (size_t(8) << 20) ? need * 2 : (size_t(8) << 20);
+                if (c->stagingHost) cudaFreeHost(c->stagingHost);
+                cudaFree(c->stagingDev);
+                c->stagingHost = nullptr; c->stagingDev = nullptr; c->stagingCap = 0;
+                HDT_CUDA(cudaMallocHost(&c->stagingHost, cap));
+                HDT_CUDA(cudaMalloc(&c->stagingDev, cap));
+                c->stagingCap = cap;
+            }
+        }
+        memcpy(c->stagingHost + c->stagingUsed, pages.data(), pages.size() * sizeof(u32));
+        HDT_CUDA(cudaMemcpyAsync(c->stagingDev + c->stagingUsed, c->stagingHost + c->stagingUsed, need, cudaMemcpyHostToDevice, c->stream));
+        dPages = reinterpret_cast<const u32*>(c->stagingDev + c->stagingUsed);
+        c->stagingUsed += need;
+        nPages = u32(pages.size());
+    }
+    resolve_pages_kernel<<<(nPages + 3) / 4, 128, 0, c->stream>>>(dag->pool, dag->page_table, c->physToVirt, dPages, nPages, HashLayoutDev{ c->levels }, resolved_pool_dev);
+    ++c->launches;
+    HDT_CUDA(cudaGetLastError());
+    return HDT_OK;
+}
+
 int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t old_leaf_size, const hdt_color_op* ops, uint64_t n_ops,
                            uint32_t* weights_out, uint64_t weights_capacity, uint64_t* blocks_out, uint64_t blocks_capacity,
                            uint64_t* macro_blocks_out, uint64_t macro_blocks_capacity, uint64_t counts_out[4], float* ms)
@@ -1341,7 +1425,8 @@ int hdt_get_values(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
     const u32 grid = u32((nCells + 127) / 128);
     if (dag.kind == HDT_DAG_BASIC) get_values_kernel<<<grid, 128, 0, c->stream>>>(dag.basic, c->levels, rp, values_dev);
-    else get_values_kernel<<<grid, 128, 0, c->stream>>>(dag.hash, c->levels, rp, values_dev);
+    else if (dag.kind == HDT_DAG_HASH) get_values_kernel<<<grid, 128, 0, c->stream>>>(dag.hash, c->levels, rp, values_dev);
+    else get_values_kernel<<<grid, 128, 0, c->stream>>>(dag.resolved, c->levels, rp, values_dev);
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     ++c->launches;
     return finish_timed(c, c->ev[0], c->ev[1], ms);
@@ -1377,7 +1462,8 @@ int hdt_is_empty(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_s
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
     const u32 grid = u32((nCells + 127) / 128);
     if (dag.kind == HDT_DAG_BASIC) is_empty_kernel<<<grid, 128, 0, c->stream>>>(dag.basic, steps, rp, found);
-    else is_empty_kernel<<<grid, 128, 0, c->stream>>>(dag.hash, steps, rp, found);
+    else if (dag.kind == HDT_DAG_HASH) is_empty_kernel<<<grid, 128, 0, c->stream>>>(dag.hash, steps, rp, found);
+    else is_empty_kernel<<<grid, 128, 0, c->stream>>>(dag.resolved, steps, rp, found);
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     ++c->launches;
     u32 host = 0;

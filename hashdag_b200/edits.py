@@ -235,7 +235,7 @@ class HashDagReplica:
     """One GPU's copy of a HashDAG (+ colours) that follows edits through deltas.  Needs CUDA."""
 
     def __init__(self, tracer_obj, pool, page_table, pool_top, first_node_index, levels, pool_capacity_pages,
-                 color_nodes=None, color_offsets=None, main_leaf=None, color_node_capacity=0, device="cuda:0"):
+                 color_nodes=None, color_offsets=None, main_leaf=None, color_node_capacity=0, device="cuda:0", resolved=True):
         import torch
         from . import tracer as T
         self._T, self._torch, self.tracer, self.device, self.levels = T, torch, tracer_obj, device, levels
@@ -244,6 +244,13 @@ class HashDagReplica:
         self.pool[: pool.size] = T._to_device(pool, device)
         self.page_table = T._to_device(page_table, device)
         self.pool_top, self.first_node_index = int(pool_top), int(first_node_index)
+        # the resolved pool (child pointers pre-translated, csrc/hdt_resolve.cuh) follows every edit page by page
+        self.resolved_pool = None
+        if resolved:
+            self.resolved_pool = torch.zeros(cap, dtype=torch.int32, device=device)
+            torch.cuda.synchronize()                    # the uploads above ran on torch's stream, the resolve runs on the tracer's
+            self.levels = levels
+            tracer_obj.resolve_hash_dag(self._hash_dag(), self.resolved_pool)
         self.has_colors = color_nodes is not None
         if self.has_colors:
             ncap = max(int(color_node_capacity), int(color_nodes.size))
@@ -265,6 +272,9 @@ class HashDagReplica:
         self.tracer.apply_ranges_host(self.pool, delta.pool_payload, delta.pool_ranges)
         self.tracer.apply_ranges_host(self.page_table, delta.table_payload, delta.table_ranges)
         self.pool_top, self.first_node_index = int(delta.pool_top), int(delta.first_node_index)
+        if self.resolved_pool is not None and len(delta.pool_ranges):
+            # pages whose words changed, plus nothing else: older nodes never point at newer ones and their pointers stay valid
+            self.tracer.resolve_hash_dag(self._hash_dag(), self.resolved_pool, delta.pool_ranges)
         if self.has_colors and delta.n_color_nodes:
             if delta.n_color_nodes > self.color_nodes.numel():
                 grown = torch.zeros(2 * delta.n_color_nodes, dtype=torch.int32, device=self.device)
@@ -306,8 +316,12 @@ class HashDagReplica:
                 self.tracer.sync()                      # frames in flight may still read the previous POD array
                 self.leaf_pods = T._to_device(self._pods_host[: delta.n_color_leaves].reshape(-1), self.device)
 
-    def dag(self):
+    def _hash_dag(self):
         return self._T.HashDAG(self.pool, self.page_table, self.pool_top, self.first_node_index, self.levels)
+
+    def dag(self):
+        d = self._hash_dag()
+        return d if self.resolved_pool is None else self._T.ResolvedHashDAG(d, self.resolved_pool)
 
     def colors(self):
         T = self._T

@@ -25,7 +25,8 @@ extern "C" {
 
 typedef struct hdt_ctx hdt_ctx;
 
-enum { HDT_DAG_BASIC = 0, HDT_DAG_HASH = 1 };
+enum { HDT_DAG_BASIC = 0, HDT_DAG_HASH = 1,
+       HDT_DAG_HASH_RESOLVED = 2 /* hdt_resolved_hash_dag: a HashDAG + its resolved pool (hdt_hash_dag_resolve); same results, shorter load chains */ };
 enum {
     HDT_COLORS_UNCOMPRESSED = 0, /* BasicDAGUncompressedColors, basic_dag.h:122-177 */
     HDT_COLORS_COMPRESSED = 1,   /* BasicDAGCompressedColors,   basic_dag.h:91-120  */
@@ -52,6 +53,11 @@ typedef struct hdt_hash_dag {                                                   
     uint32_t first_node_index;
     uint32_t _pad;
 } hdt_hash_dag;
+
+typedef struct hdt_resolved_hash_dag {      /* library format, 40 B: the HashDAG as the reference passes it + a copy of its pool in which every */
+    hdt_hash_dag dag;                        /* child pointer already holds the child's physical word index (hdt_hash_dag_resolve)               */
+    const uint32_t* resolved_pool;           /* device, pool_top * 512 words, caller-owned */
+} hdt_resolved_hash_dag;
 
 typedef struct hdt_color_leaf {                                                                /* CompressedColorLeaf, vwsc.h:157-191: 104 B */
     uint64_t offset;              /* offset into the shared leaf; UINT64_MAX = unique */
@@ -237,6 +243,15 @@ int hdt_is_empty(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod
  * (hash_table.cpp:120-184) and its closing cudaDeviceSynchronize. */
 int hdt_apply_ranges_host(hdt_ctx* ctx, uint32_t* dst_dev, const uint32_t* payload_host, uint64_t n_payload_words,
                           const hdt_range* ranges_host, uint32_t n_ranges);
+
+/* Fill (ranges_host == NULL: all pool_top pages) or refresh (the pages the n_ranges pool spans of an edit touch, as
+ * given to hdt_apply_ranges[_host]) `resolved_pool_dev`, a caller-owned device buffer of pool_top * 512 words
+ * (capacity_words >= that): a copy of the HashDAG's pool with the same physical layout whose child pointers have been
+ * pushed through the page table once.  Pass it with the DAG as hdt_resolved_hash_dag / HDT_DAG_HASH_RESOLVED wherever a
+ * HashDAG is accepted: a descent then costs two dependent loads instead of three; frames are identical.  Call it after the
+ * pool and page table of an edit have been applied; asynchronous (tracer's stream, ordered before later frames). */
+int hdt_hash_dag_resolve(hdt_ctx* ctx, const hdt_hash_dag* dag, size_t dag_size, uint32_t* resolved_pool_dev, uint64_t capacity_words,
+                         const hdt_range* ranges_host, uint32_t n_ranges);
 
 /* Kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t hdt_launch_count(const hdt_ctx* ctx);

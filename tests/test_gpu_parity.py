@@ -205,6 +205,53 @@ def test_partitioned_render_assembles_to_the_whole_frame(tr):
     t0.close()
 
 
+@pytest.mark.parametrize("levels", [13, 17])
+def test_resolved_hash_dag_gives_the_same_frames(tr, levels):
+    """HDT_DAG_HASH_RESOLVED (child pointers pre-translated, csrc/hdt_resolve.cuh) against the plain HashDAG: paths,
+    every colour view, shaded and fogged frames, beams on and off, and the region queries."""
+    import torch
+    from hashdag_b200 import tracer
+    s = get_scene(levels, 10)
+    t = tr(levels)
+    dag, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
+    res = t.resolve_hash_dag(dag)
+    assert res.kind == tracer.DAG_HASH_RESOLVED and len(res.pod()) == 40
+    info = _info(s)
+    # the resolved pool differs from the pool exactly in the child-pointer words
+    t.sync()
+    a, b = dag.pool.cpu().numpy().view(np.uint32), res.resolved_pool.cpu().numpy().view(np.uint32)
+    assert a.shape == b.shape and 0 < int((a != b).sum()) < a.size
+    for beams in (1, 0):
+        t.set_option(tracer.OPT_BEAMS, beams)
+        for cam in scene_cameras(s, 2, 10) + _special_cameras(s, 10)[:2]:
+            frames = []
+            for d in (dag, res):
+                t.resolve_paths(cam, info, d)
+                p = t.read_paths()
+                views = []
+                for dbg, lvl in ((tracer.DEBUG_NONE, 0), (tracer.DEBUG_INDEX, 3), (tracer.DEBUG_INDEX, levels - 2), (tracer.DEBUG_POSITION, 0),
+                                 (tracer.DEBUG_COLOR_TREE, 0), (tracer.DEBUG_WEIGHT, 0)):
+                    t.resolve_colors(d, col, dbg, lvl)
+                    views.append(t.read_colors())
+                t.resolve_colors(d, col)
+                t.resolve_shadows(cam, info, d, 1.0, 0.0)
+                sh = t.read_colors()
+                t.resolve_colors(d, col)
+                t.resolve_shadows(cam, info, d, 1.0, 4.0)
+                frames.append((p, views, sh, t.read_colors()))
+            (p0, v0, s0, f0), (p1, v1, s1, f1) = frames
+            assert np.array_equal(p0, p1) and np.array_equal(s0, s1) and np.array_equal(f0, f1)
+            for x, y in zip(v0, v1):
+                assert np.array_equal(x, y)
+    t.set_option(tracer.OPT_BEAMS, 1)
+    c = 1 << (levels - 1)
+    h0 = int(s.heights[(c, c)])
+    st, sz = (c - 20, h0 - 16, c - 20), (50, 40, 45)
+    assert torch.equal(t.get_values(dag, st, sz)[0], t.get_values(res, st, sz)[0])
+    for lvl in range(levels - 1):
+        assert t.is_empty(dag, lvl, st, sz) == t.is_empty(res, lvl, st, sz)
+
+
 class _DevMem:
     def __init__(self, ptr, count):
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
