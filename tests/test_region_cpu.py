@@ -47,3 +47,23 @@ def test_get_values_is_the_point_query_strictly_inside_the_region():
         x, y, z = (int(rng.integers(0, s)) for s in sz)
         want = region.get_value(dag, (st[0] + x, st[1] + y, st[2] + z)) and min(x, y, z) > 0
         assert bool(v[z, y, x]) == want
+
+
+def test_every_traced_path_is_a_voxel_of_the_dag():
+    """SURVEY.md §8c invariant (ii): DAGUtils::get_value(dag, path) holds for every non-null path trace_paths returns
+    (oracle frame, BasicDAG and HashDAG), and fails one voxel above the terrain's highest hit."""
+    from hashdag_b200 import camera
+    from oracle import hdo
+    scene = gu.recipe_scene("d13")
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    pose = gu.recipe_poses(scene)[0]
+    prm = camera.trace_params(pose, info, scene.levels, 96, 96)
+    for kind, dk in (("basic", hdo.DAG_BASIC), ("hash", hdo.DAG_HASH)):
+        paths, _ = hdo.trace_paths(hdo.make_dag(scene, dk), 96, 96, prm)
+        hit = paths[..., :3][paths[..., :3].any(-1)]
+        assert hit.shape[0] > 2000
+        dag = region.HostDag.from_scene(scene, kind)
+        for p in hit[:: max(1, hit.shape[0] // 500)]:
+            assert region.get_value(dag, tuple(int(v) for v in p))
+        top = hit[hit[:, 1].argmax()]
+        assert not region.get_value(dag, (int(top[0]), int(top[1]) + 300, int(top[2])))
