@@ -45,8 +45,9 @@ def parse_args():
     ap.add_argument("--dag", default="hash", choices=["hash", "basic"])
     ap.add_argument("--no-beam-prefetch", action="store_true", help="keep the beam kernels of frame n+1 behind all of frame n")
     ap.add_argument("--no-resolved", action="store_true", help="trace the HashDAG through its page table (A/B); default: the resolved pool (hdt_hash_dag_resolve)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: how the tiles reach rank 0's frame -- stores over peer memory (hdt_exchange_*, default) or NCCL gather + assembly (A/B)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-fused", "nccl"],
+                    help="N > 1: how the tiles reach rank 0's frame -- stored over peer memory by a scatter kernel (default), by the shadows kernel "
+                         "itself (peer-fused, HDT_OPT_EXCHANGE_FUSED), or NCCL gather + assembly (A/B)")
     ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
                     help="tracer contexts (each with its own streams and frame buffers) the fly-through alternates between")
     return ap.parse_args()
@@ -166,7 +167,7 @@ def workload_config(args, scene, W, H, world):
         "levels": args.levels, "resolution": [W, H], "voxels": int(scene.n_voxels), "dag_words": int(scene.basic.size),
         "hash_pool_mib": round(scene.hash_pool.nbytes / 2**20, 1) if scene.has_hash else 0,
         "color_mib": round((scene.weights.nbytes + scene.blocks.nbytes + scene.macro_blocks.nbytes) / 2**20, 1),
-        "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, " + ("tiles stored into rank 0's frame over NVLink peer memory" if getattr(args, "exchange", "peer") == "peer" else "NCCL gather to rank 0"),
+        "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, " + ("NCCL gather to rank 0" if getattr(args, "exchange", "peer") == "nccl" else "tiles stored into rank 0's frame over NVLink peer memory"),
         "l2_policy": "inputs larger than L2: each step is a different camera pose over a DAG pool >> 126 MB",
         "shadow_bias": 1.0, "fog_density": 0.0,
         "beam_prefetch": not getattr(args, "no_beam_prefetch", False),
@@ -303,7 +304,8 @@ def run_ours(args):
             t_.set_stream(s_.cuda_stream)
         frame = frames[0] if rank == 0 else None
 
-        if args.exchange == "peer":
+        peer = args.exchange in ("peer", "peer-fused")
+        if peer:
             # rank 0's frames are mapped into every rank (CUDA IPC); ranks store their tiles into them (csrc/hdt_exchange.cuh)
             frames = []
             for t_ in lanes:
@@ -323,7 +325,7 @@ def run_ours(args):
         def gather(k, release=True):
             if os.environ.get("HDT_BENCH_NO_GATHER"):      # diagnostics only: how much of a step is the exchange
                 return
-            if args.exchange == "peer":
+            if peer:
                 lanes[k].exchange_frame()
                 if rank == 0 and release:
                     lanes[k].exchange_release()
@@ -368,6 +370,12 @@ def run_ours(args):
     # beside the colours / shadows kernels of frame n (include/hashdag_b200.h, HDT_OPT_BEAM_PREFETCH).
     for t_ in lanes:
         t_.set_option(tracer.OPT_BEAM_PREFETCH, 0 if args.no_beam_prefetch else 1)
+
+    def arm_fused(on):
+        if world > 1 and args.exchange == "peer-fused" and not os.environ.get("HDT_BENCH_NO_GATHER"):
+            for t_ in lanes:
+                t_.set_option(tracer.OPT_EXCHANGE_FUSED, 1 if on else 0)
+    arm_fused(True)     # from here on every frame with shadows is followed by its exchange
 
     # ---- warm-up ------------------------------------------------------------------------------
     for i in range(args.warmup):
@@ -443,7 +451,7 @@ def run_ours(args):
             if rank == 0:
                 with torch.cuda.stream(streams[k]):
                     host_frames[k].copy_(frames[k], non_blocking=True)
-                if args.exchange == "peer":
+                if peer:
                     lanes[k].exchange_release()          # after the copy on the same stream: the peers may overwrite frame k
     sync_all()
     barrier()
@@ -454,6 +462,8 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_value = rays / (e2e_ms * 1e-3) / 1e6
 
+    sync_all()
+    arm_fused(False)    # the pass timings below render frames that are not exchanged
     # ---- per-pass kernel times on the sample poses (for the roofline) ------------------------
     sample_ids = [int(k * len(poses) / max(1, args.cpu_sample_poses)) for k in range(args.cpu_sample_poses)]
     pass_ms = {i: [0.0, 0.0, 0.0] for i in sample_ids}
@@ -482,6 +492,7 @@ def run_ours(args):
     exchange_mismatch = None
     if world > 1 and not os.environ.get("HDT_BENCH_NO_GATHER"):
         exchange_mismatch = 0
+        arm_fused(True)
         whole = tracer.DAGTracer(True, W, H, args.levels, device=local_rank) if rank == 0 else None
         for i in sample_ids[:2]:
             lanes[0].enqueue_frame(params[i], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
@@ -489,7 +500,7 @@ def run_ours(args):
             if rank == 0:
                 with torch.cuda.stream(streams[0]):
                     host_frame.copy_(frames[0], non_blocking=True)
-                if args.exchange == "peer":
+                if peer:
                     lanes[0].exchange_release()
             lanes[0].sync()
             streams[0].synchronize()
@@ -516,7 +527,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "setup_s": round(t_build, 1), "scene_build_s": round(scene.build_seconds, 1), "replication_bytes": int(replication_bytes),
-        "timing": ("cudaEvents on the tracer streams around K enqueued frames; two frames in flight, " + ("tiles stored into rank 0's frame over peer memory (hdt_exchange_*)" if args.exchange == "peer" else "NCCL gather + assembly") + " included, max over ranks" if gather
+        "timing": ("cudaEvents on the tracer streams around K enqueued frames; two frames in flight, " + ({"peer-fused": "tiles stored into rank 0's frame over peer memory by trace_shadows_kernel (hdt_exchange_*, fused)", "peer": "tiles stored into rank 0's frame over peer memory by a scatter kernel (hdt_exchange_*)", "nccl": "NCCL gather + assembly"}[args.exchange]) + " included, max over ranks" if gather
                    else f"cudaEvents on the tracer streams around K enqueued frames, {len(lanes)} frame(s) in flight"),
         "wall_ms_per_step": wall_ms / args.steps,
     }

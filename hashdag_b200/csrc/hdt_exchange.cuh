@@ -14,6 +14,10 @@
 
 namespace hdt {
 
+// What a fused final pass needs: rank 0's frame (nullptr = not fused), this context's last-CTA counter, and rank 0's
+// arrival counter (nullptr on rank 0 itself, which does not signal).
+struct ExchangeOut { u32* frame; u32* ctasDone; u32* arrivals; };
+
 struct ExchangeCounters { u32 arrivals; u32 credit; u32 pad[62]; };   // 256 B, lives behind the frame
 
 __device__ __forceinline__ u32 load_volatile(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
@@ -42,6 +46,22 @@ __global__ void exchange_signal_kernel(u32* arrivals)   // a rank that owns no t
     atomicAdd_system(arrivals, 1u);
 }
 
+// End of a kernel that stored into rank 0's frame: make the CTA's stores visible system-wide, count the CTA, and let the
+// last one bump `arrivals` in rank 0's memory.  Every thread of the CTA must call it.
+__device__ __forceinline__ void exchange_signal_last_cta(u32* __restrict__ ctasDone, u32* arrivals)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u32 prev = atomicAdd(ctasDone, 1u);
+        if (prev == gridDim.x - 1) {
+            *ctasDone = 0;                            // ready for the next launch (stream order separates launches)
+            __threadfence_system();
+            if (arrivals) atomicAdd_system(arrivals, 1u);
+        }
+    }
+}
+
 // This rank's compact tiles (each (1<<tileLog2)^2 pixels, row-major, owned tiles back to back) -> the row-major frame,
 // which may live in another GPU's memory.  One CTA per 16 tile rows; the last CTA to finish signals `arrivals`.
 __global__ void __launch_bounds__(256) exchange_scatter_kernel(const u32* __restrict__ compact, u32* __restrict__ frame, const PixelMap map,
@@ -67,16 +87,7 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const u32* __rest
             if (y < map.height && x < map.width) frame[u64(y) * map.width + x] = src[r * T + c];
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const u32 prev = atomicAdd(ctasDone, 1u);
-        if (prev == gridDim.x - 1) {
-            *ctasDone = 0;                            // ready for the next launch (stream order separates launches)
-            __threadfence_system();
-            if (arrivals) atomicAdd_system(arrivals, 1u);
-        }
-    }
+    exchange_signal_last_cta(ctasDone, arrivals);
 }
 
 }  // namespace hdt

@@ -257,23 +257,16 @@ __global__ void __launch_bounds__(32) beam_shadows_kernel(const ShadowParams sp,
 }
 
 template <class DAG>
-__global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
-                                                                      const PixelMap map, const uint4* __restrict__ paths, const RayPlanes origins,
-                                                                      u32* __restrict__ colors, const TraverseTables* __restrict__ tables,
-                                                                      const BeamState* __restrict__ beams, const u32 tag)
+__device__ __forceinline__ void shadow_pixel(const CameraParams& cam, const ShadowParams& sp, const DAG& dag, const u32 levels, const PixelMap& map,
+                                             const uint4* __restrict__ paths, const RayPlanes& origins, u32* __restrict__ colors, const TraverseTables& tab,
+                                             const BeamState* bs, const u32 status, const u32 x, const u32 y, u32* __restrict__ xFrame)
 {
-    __shared__ TraverseTables tab;
-    load_tables(tab, tables);
-    const BeamState* bs = beams ? beams + (blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)) : nullptr;
-    const u32 status = beam_status(bs, tag);   // whole warp, before anybody leaves
-#ifdef HDT_BEAM_DEBUG
-    if (beams && (threadIdx.x & 31) == 0) atomicAdd(&g_beamDebug[4 + status], 1u);
-#endif
-    __syncthreads();
-    u32 x, y;
-    if (!thread_pixel(map, x, y)) return;
     const u64 idx = map.index(x, y);
     const uint4 p = paths[idx];
+    auto put = [&](u32 rgba) {
+        colors[idx] = rgba;
+        if (xFrame) xFrame[u64(y) * map.width + x] = rgba;
+    };
 
     // setColor (tracer.cu:604-619) + applyFog (:551-572); contraction as in the reference PTX.
     // hit == false: sky pixel, distance 1e9 along the primary direction (tracer.cu:644-648).
@@ -285,7 +278,7 @@ __global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_shadows_k
             // No fog: fogAmount = 1 - exp(-0) = 0 exactly, so lerp(lit, fogColor, 0) = fma(lit, 1, 0*fogColor) = lit
             // bit for bit (fogColor is finite); distance, direction, exp and pow of applyFog cannot change the
             // result and are not computed.
-            colors[idx] = float3_to_rgb888(lx, ly, lz);
+            put(float3_to_rgb888(lx, ly, lz));
             return;
         }
         double distance = 1e9, rdx, rdy, rdz;
@@ -303,7 +296,7 @@ __global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_shadows_k
         const float pw = __double2float_rn(pow(sunAmount, 30.0)), q = __fsub_rn(1.f, pw);
         const float fx = __fmaf_rn(q, __fdiv_rn(187.f, 255.f), pw), fy = __fmaf_rn(q, __fdiv_rn(242.f, 255.f), pw), fz = __fmaf_rn(q, __fdiv_rn(250.f, 255.f), pw);
         const float g = clampf(__double2float_rn(fogAmount), 0.f, 1.f), h = __fsub_rn(1.f, g);
-        colors[idx] = float3_to_rgb888(__fmaf_rn(lx, h, __fmul_rn(g, fx)), __fmaf_rn(ly, h, __fmul_rn(g, fy)), __fmaf_rn(lz, h, __fmul_rn(g, fz)));
+        put(float3_to_rgb888(__fmaf_rn(lx, h, __fmul_rn(g, fx)), __fmaf_rn(ly, h, __fmul_rn(g, fy)), __fmaf_rn(lz, h, __fmul_rn(g, fz))));
     };
     if ((p.x | p.y | p.z) == 0) { shade(1.0f, false); return; }
 
@@ -321,6 +314,27 @@ __global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_shadows_k
                                          : traverse<DAG, false, false>(dag, levels, ray, tab, 0, hx, hy, hz);
     }
     shade(shadowed ? 0.5f : 1.0f, true);
+}
+
+template <class DAG>
+__global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
+                                                                      const PixelMap map, const uint4* __restrict__ paths, const RayPlanes origins,
+                                                                      u32* __restrict__ colors, const TraverseTables* __restrict__ tables,
+                                                                      const BeamState* __restrict__ beams, const u32 tag, const ExchangeOut xo)
+{
+    __shared__ TraverseTables tab;
+    load_tables(tab, tables);
+    const BeamState* bs = beams ? beams + (blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5)) : nullptr;
+    const u32 status = beam_status(bs, tag);   // whole warp, before anybody leaves
+#ifdef HDT_BEAM_DEBUG
+    if (beams && (threadIdx.x & 31) == 0) atomicAdd(&g_beamDebug[4 + status], 1u);
+#endif
+    __syncthreads();
+    u32 x, y;
+    if (thread_pixel(map, x, y)) shadow_pixel<DAG>(cam, sp, dag, levels, map, paths, origins, colors, tab, bs, status, x, y, xo.frame);
+    // Fused framebuffer exchange (hdt_exchange.cuh): the pixel above also went into rank 0's row-major frame; the last CTA
+    // of the launch tells rank 0 that this rank's tiles are complete.
+    if (xo.frame) exchange_signal_last_cta(xo.ctasDone, xo.arrivals);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -434,6 +448,9 @@ struct hdt_ctx {
     u32* xBlock = nullptr;              // [frame W*H][ExchangeCounters]: own allocation (root) or a mapping of the root's
     bool xOwned = false, xIpc = false;
     u32 xSeq = 0;                       // frames exchanged on this context
+    bool xFused = false;                // HDT_OPT_EXCHANGE_FUSED: shadow passes store into rank 0's frame themselves
+    u32 xFusedSeq = 0;                  // sequence number the last fused shadow pass stored for
+    u32* xTimedOutDev = nullptr;        // device alias of xTimedOut
     u32* xCtasDone = nullptr;           // device, scatter kernel's last-CTA counter
     u32* xTimedOut = nullptr;           // pinned + mapped: raised by a wait kernel that gave up
     char* stagingHost = nullptr;        // hdt_apply_ranges_host: pinned + device staging, bump-allocated, reset when full
@@ -690,9 +707,21 @@ void finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const 
     if (!prep.valid) return;
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[1] : c->setupDone[1], 0);   // the origins
-    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
-    else if (d.kind == HDT_DAG_HASH) trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
-    else trace_shadows_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, sp, d.resolved, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag);
+    // Fused framebuffer exchange: this pass writes the final colours, so it can store them into rank 0's frame itself.
+    ExchangeOut xo{ nullptr, nullptr, nullptr };
+    if (c->xFused && c->xBlock) {
+        const u32 seq = c->xSeq + 1;
+        ExchangeCounters* k = reinterpret_cast<ExchangeCounters*>(reinterpret_cast<char*>(c->xBlock) + ((size_t(c->map.width) * c->map.height * 4 + 255) & ~size_t(255)));
+        if (c->map.rank != 0) {   // rank 0 must have consumed the previous frame of this lane
+            exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, c->xTimedOutDev);
+            ++c->launches;
+        }
+        xo = ExchangeOut{ c->xBlock, c->xCtasDone, c->map.rank != 0 ? &k->arrivals : nullptr };
+        c->xFusedSeq = seq;
+    }
+    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
+    else if (d.kind == HDT_DAG_HASH) trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
+    else trace_shadows_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, sp, d.resolved, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
     cudaEventRecord(c->traceDone[1], c->stream);
     ++c->launches;
     cudaStreamWaitEvent(c->stream, c->join[1], 0);
@@ -808,6 +837,7 @@ int hdt_set_option(hdt_ctx* c, int option, int value)
     if (option == HDT_OPT_BEAMS) { c->useBeams = value != 0; return HDT_OK; }
     if (option == HDT_OPT_BEAM_PREFETCH) { c->beamPrefetch = value != 0; return HDT_OK; }
     if (option == HDT_OPT_BEAM_SERIAL) { c->beamSerial = value != 0; return HDT_OK; }
+    if (option == HDT_OPT_EXCHANGE_FUSED) { c->xFused = value != 0; return HDT_OK; }
     if (option == HDT_OPT_BEAM_MAX_VISITS) { if (value < 1) return fail(HDT_ERR_ARG, "beam visit cap must be >= 1"); c->beamMaxVisits = u32(value); return HDT_OK; }
     return fail(HDT_ERR_ARG, "unknown option");
 }
@@ -1113,8 +1143,9 @@ int exchange_common(hdt_ctx* c)
     if (!c->xTimedOut) {
         HDT_CUDA(cudaHostAlloc(&c->xTimedOut, sizeof(u32), cudaHostAllocMapped));
         *c->xTimedOut = 0;
+        HDT_CUDA(cudaHostGetDevicePointer(&c->xTimedOutDev, c->xTimedOut, 0));
     }
-    c->xSeq = 0;
+    c->xSeq = 0; c->xFusedSeq = 0;
     return HDT_OK;
 }
 }  // namespace
@@ -1180,19 +1211,19 @@ int hdt_exchange_frame(hdt_ctx* c)
     HDT_CUDA(cudaSetDevice(c->device));
     const u32 seq = ++c->xSeq;
     ExchangeCounters* k = exchange_counters(c);
-    u32* timedOutDev = nullptr;
-    HDT_CUDA(cudaHostGetDevicePointer(&timedOutDev, c->xTimedOut, 0));
+    u32* timedOutDev = c->xTimedOutDev;
     const u32 T = 1u << c->map.tileLog2;
-    const u32 grid = c->nOwnedTiles * (T / 16);
+    const bool fused = c->xFusedSeq == seq && c->grid_blocks() > 0;   // the last shadow pass already stored (and signalled) this frame
+    const u32 grid = fused ? 0 : c->nOwnedTiles * (T / 16);
     const bool root = c->map.rank == 0;
-    if (!root) {   // the root must have consumed the previous frame of this lane before it is overwritten
+    if (!root && !fused) {   // the root must have consumed the previous frame of this lane before it is overwritten
         exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, timedOutDev);
         ++c->launches;
     }
     if (grid) {
         exchange_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->colors, c->xBlock, c->map, c->xCtasDone, root ? nullptr : &k->arrivals);
         ++c->launches;
-    } else if (!root) {
+    } else if (!root && !fused) {
         exchange_signal_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals);
         ++c->launches;
     }

@@ -120,7 +120,10 @@ enum {
                                     in flight (hdt_resolve_frame_async) they run beside the previous frame's colours / shadows.
                                     Only valid while nothing queued on the tracer's stream modifies the DAG (static scene, or
                                     edits applied after hdt_sync()).  env HDT_BEAM_PREFETCH */
-    HDT_OPT_BEAM_SERIAL = 4      /* diagnostics, default 0.  1: the per-ray kernels wait for the beam kernel instead of racing it */
+    HDT_OPT_BEAM_SERIAL = 4,     /* diagnostics, default 0.  1: the per-ray kernels wait for the beam kernel instead of racing it */
+    HDT_OPT_EXCHANGE_FUSED = 5   /* default 0.  1 (needs an exchange, hdt_exchange_*): every shadows pass -- the pass that writes a frame's final
+                                    colours -- also stores them into rank 0's frame and its last CTA signals the arrival, so hdt_exchange_frame has
+                                    nothing left to copy.  While set, every shadows pass must be followed by hdt_exchange_frame. */
 };
 int hdt_set_option(hdt_ctx* ctx, int option, int value);
 /* Diagnostics of the last beam pre-pass: out[0..3] = tiles that start at the root / resume below it /

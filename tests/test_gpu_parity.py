@@ -257,8 +257,10 @@ class _DevMem:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
-def test_peer_exchange_assembles_the_whole_frame(tr):
-    """hdt_exchange_*: three ranks (contexts of this process, attached by pointer) store their tiles straight into rank
+@pytest.mark.parametrize("fused", [0, 1])
+def test_peer_exchange_assembles_the_whole_frame(tr, fused):
+    """fused = 1: trace_shadows_kernel stores the final colours into rank 0's frame itself (HDT_OPT_EXCHANGE_FUSED).
+    hdt_exchange_*: three ranks (contexts of this process, attached by pointer) store their tiles straight into rank
     0's frame; arrivals / credit counters order the frames.  Three frames in a row == the unpartitioned frames."""
     import torch
     from hashdag_b200 import tracer
@@ -275,6 +277,8 @@ def test_peer_exchange_assembles_the_whole_frame(tr):
     _, frame_ptr = ranks[0].exchange_create()
     for t in ranks[1:]:
         t.exchange_attach(ranks[0].exchange_block())
+    for t in ranks:
+        t.set_option(tracer.OPT_EXCHANGE_FUSED, fused)
     frame = torch.as_tensor(_DevMem(frame_ptr, W * H), device="cuda")
     info = _info(s)
     for cam in cams:
