@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-fused", "nccl"],
                     help="N > 1: how the tiles reach rank 0's frame -- stored over peer memory by a scatter kernel (default), by the shadows kernel "
                          "itself (peer-fused, HDT_OPT_EXCHANGE_FUSED), or NCCL gather + assembly (A/B)")
-    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--frames-in-flight", type=int, default=3, choices=[1, 2, 3, 4],
                     help="tracer contexts (each with its own streams and frame buffers) the fly-through alternates between")
     return ap.parse_args()
 
@@ -334,10 +334,10 @@ def run_ours(args):
                 dist.gather(mine[k], list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
                 if rank == 0:
                     lanes[k].assemble_colors(gathered[k], frames[k])
-    elif args.frames_in_flight == 2:
+    elif args.frames_in_flight >= 2:
         # single GPU: frame i+1 (second context, own streams and buffers) is enqueued while frame i runs, so the
         # drain of one kernel overlaps the ramp-up of another instead of leaving SMs idle
-        lanes = [tr, tracer.DAGTracer(True, W, H, args.levels, device=local_rank)]
+        lanes = [tr] + [tracer.DAGTracer(True, W, H, args.levels, device=local_rank) for _ in range(args.frames_in_flight - 1)]
     host_frame = torch.empty(W * H, dtype=torch.int32).pin_memory() if rank == 0 else None
 
     def barrier():
