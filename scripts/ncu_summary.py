@@ -43,7 +43,7 @@ per_pass = {}
 for p in ("paths", "shadows", "colors"):
     tot = 0.0
     for n, d in kernels.items():
-        if p in n and "HashDagDev" in n or (p in n and "setup_" in n):
+        if p in n and ("HashDagDev" in n or "HashDagResolvedDev" in n) or (p in n and "setup_" in n):
             tot += (d.get("dram_read_MB", 0) + d.get("dram_write_MB", 0)) * 1e6
     per_pass[p] = tot
 json.dump({"source": rep + " (ncu --set full --clock-control none; per-launch averages; cold caches, kernels serialised)",
