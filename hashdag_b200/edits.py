@@ -169,6 +169,41 @@ def delta_from_bucket_sizes(layout: HashLayout, last_sizes, sizes, cpu_pool, pag
     return DagDelta(int(first_node_index), int(pool_top), ranges, payload, tr, tp)
 
 
+def resolve_pool_host(layout: HashLayout, pool, page_table, pool_top: int, pages=None) -> np.ndarray:
+    """Host mirror of resolve_pages_kernel (csrc/hdt_resolve.cuh): the pool with every child pointer replaced by the child's
+    physical word index.  Pages are parsed on their own: a virtual page belongs to one level (hash_table.h:45-63); interior
+    nodes `[header][pointer] x popc(header & 0xFF)` are packed from the start of a page, never straddle one and the tail is
+    zero padding (add_interior_node, hash_table.h:416-430); pages of level >= levels-2 hold 64-bit leaves and are copied.
+    `pages`: physical pages to resolve (default all below pool_top); the others are returned unchanged."""
+    P = layout.PAGE
+    pool = np.asarray(pool)
+    out = pool[: pool_top * P].copy()
+    page_table = np.asarray(page_table)
+    used = np.flatnonzero(page_table)
+    used = used[page_table[used] < pool_top]
+    virt_of = np.full(pool_top, -1, dtype=np.int64)
+    virt_of[page_table[used]] = used
+    top_pages = min(9, layout.levels) * 1024 * (1024 // P)
+    for p in (range(pool_top) if pages is None else pages):
+        v = int(virt_of[p])
+        if v < 0:
+            continue
+        level = v // (1024 * (1024 // P)) if v < top_pages else 9 + (v - top_pages) // (65536 * (4096 // P))
+        if level >= layout.levels - 2:
+            continue
+        words = pool[p * P:(p + 1) * P]
+        pos = 0
+        while pos < P:
+            hdr = int(words[pos])
+            if hdr & 0xFF == 0:
+                break
+            n = bin(hdr & 0xFF).count("1")
+            ptrs = words[pos + 1: pos + 1 + n].astype(np.int64)
+            out[p * P + pos + 1: p * P + pos + 1 + n] = (page_table[ptrs >> 9].astype(np.int64) * P + (ptrs & (P - 1))).astype(np.uint32)
+            pos += 1 + n
+    return out
+
+
 def add_color_delta(d: "DagDelta", old_color_nodes, new_color_nodes, old_leaves, new_leaves) -> "DagDelta":
     """Colour part of a delta (tree nodes + rebuilt unique leaves), as in diff_hash_dag."""
     d.color_node_ranges, d.color_node_payload = dirty_spans(old_color_nodes if old_color_nodes is not None else np.zeros(0, np.uint32), new_color_nodes)

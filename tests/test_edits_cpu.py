@@ -122,3 +122,47 @@ def test_bucket_size_tracker_reproduces_the_arrays_without_comparing_them():
         last = sizes.copy()
     none = edits.delta_from_bucket_sizes(layout, sizes, sizes, pool, table, 7, top)
     assert len(none.pool_ranges) == 0 and len(none.table_ranges) == 0
+
+
+def test_resolved_pool_host_mirror_against_a_walk_of_the_dag():
+    """resolve_pool_host parses pages on their own (what resolve_pages_kernel does).  Ground truth: walk the HashDAG from
+    its root through the page table; every child-pointer word met on the way must hold the child's physical index in the
+    resolved pool, every other reachable word must be unchanged, and walking the resolved pool must meet the same nodes."""
+    import golden_util as gu
+    scene = gu.recipe_scene("d13")
+    layout = edits.HashLayout(scene.levels)
+    pool, table, top = scene.hash_pool, scene.hash_page_table, int(scene.hash_pool_top)
+    res = edits.resolve_pool_host(layout, pool, table, top)
+    assert res.shape == (top * 512,) and res.dtype == np.uint32
+    phys = lambda v: int(table[v >> 9]) * 512 + (v & 511)
+    leaf_level = scene.levels - 2
+    frontier = {scene.hash_first_node_index}
+    pointer_words = 0
+    for level in range(leaf_level):
+        nxt = set()
+        for v in frontier:
+            h = phys(v)
+            hdr = int(pool[h])
+            assert res[h] == hdr                                    # headers are copied
+            n = bin(hdr & 0xFF).count("1")
+            for k in range(1, n + 1):
+                child = int(pool[h + k])
+                assert int(res[h + k]) == phys(child)               # pointers are translated, once
+                nxt.add(child)
+                pointer_words += 1
+        frontier = nxt
+        if len(frontier) > 4000:                                   # bounded: a sample of every level is enough below the top
+            frontier = set(sorted(frontier)[:: len(frontier) // 4000 + 1])
+    for v in list(frontier)[:2000]:                                 # leaves: 64-bit masks, copied
+        h = phys(v)
+        assert res[h] == pool[h] and res[h + 1] == pool[h + 1]
+    assert pointer_words > 20000
+    # only pointer words differ, and resolving a subset of pages leaves the others as they are
+    changed = np.flatnonzero(res != pool[: top * 512])
+    assert 0 < changed.size
+    some = sorted(set((changed[:: max(1, changed.size // 50)] // 512).tolist()))
+    part = edits.resolve_pool_host(layout, pool, table, top, pages=some)
+    mask = np.zeros(top * 512, bool)
+    for p in some:
+        mask[p * 512:(p + 1) * 512] = True
+    assert np.array_equal(part[mask], res[mask]) and np.array_equal(part[~mask], pool[: top * 512][~mask])

@@ -221,6 +221,10 @@ def test_resolved_hash_dag_gives_the_same_frames(tr, levels):
     t.sync()
     a, b = dag.pool.cpu().numpy().view(np.uint32), res.resolved_pool.cpu().numpy().view(np.uint32)
     assert a.shape == b.shape and 0 < int((a != b).sum()) < a.size
+    if levels == 13:   # word for word the host mirror of the kernel (itself checked against a walk of the DAG in test_edits_cpu.py)
+        from hashdag_b200 import edits
+        top = int(s.hash_pool_top)
+        assert np.array_equal(b[: top * 512], edits.resolve_pool_host(edits.HashLayout(levels), s.hash_pool, s.hash_page_table, top))
     for beams in (1, 0):
         t.set_option(tracer.OPT_BEAMS, beams)
         for cam in scene_cameras(s, 2, 10) + _special_cameras(s, 10)[:2]:
