@@ -284,16 +284,22 @@ struct Walker {
         const u32 child = ORDERED ? u32(tab.child[(order << 8) | vm]) : (31 - __clz(vm));
         const float4 st = tab.step[child];
         vm &= ~__float_as_uint(st.w);
-        if (vm) { stack[level] = make_uint2(handle, cm | (vm << 8)); pending |= 1u << level; }
+        if (vm) { stack[level] = make_uint2(handle, (cm & 0xFF) | (vm << 8)); pending |= 1u << level; }
         radius = __fmul_rn(radius, 0.5f);
         cx = __fmaf_rn(st.x, radius, cx); cy = __fmaf_rn(st.y, radius, cy); cz = __fmaf_rn(st.z, radius, cz);
         ++level;
         if (level == levels) return 1;
+        // The child's header is loaded here but not touched before the ~90 instructions of mask arithmetic (which need
+        // nothing from memory) have been issued: `cm` keeps the whole header word (count24 rides along above bit 7) and the
+        // first instruction that reads it is the LOP3 that also needs the finished mask, so the load's latency hides behind
+        // the arithmetic.  (With `cm = header & 0xFF` the AND sat right behind the LDG in the SASS and the warp stalled
+        // there, in front of the arithmetic.)  Users of cm: popc(cm & (bit - 1)) with bit <= 0x80, and the stack push,
+        // which masks it.
         if (level <= leafLevel) {
             const u32 next = dag.child(handle, __popc(cm & (__float_as_uint(st.w) - 1u)) + 1);
             if (level < leafLevel) {
                 handle = next;
-                cm = dag.header(next) & 0xFF;
+                cm = dag.header(next);
             } else {
                 leaf = dag.leaf(next);
                 cm = first_child_mask(leaf);
@@ -301,7 +307,7 @@ struct Walker {
         } else {
             cm = second_child_mask(leaf, child);
         }
-        vm = cm & intersection_mask<false, TAME>(cx, cy, cz, radius, ray);
+        vm = cm & intersection_mask<false, TAME>(cx, cy, cz, radius, ray) & 0xFF;
         return 0;
     }
     // voxel coordinates once step() returned 1: centre = corner + 0.5
