@@ -4,6 +4,10 @@
 #pragma once
 #include "hdt_device.cuh"
 
+#ifndef HDT_COLORS_HOIST
+#define HDT_COLORS_HOIST 0
+#endif
+
 namespace hdt {
 
 constexpr u64 kColorsPerMacroBlock = 16 * 1024;  // vwsc.h:8
@@ -187,6 +191,11 @@ __device__ u32 color_pixel(const DAG& dag, const ColorsDev& col, const u32 level
         const u32 child = (((px >> sh) & 1) << 2) | (((py >> sh) & 1) << 1) | ((pz >> sh) & 1);
         if (!(childMask & (1u << child))) return set(0xFF00FF);
         const u32 childOff = __popc(childMask & ((1u << child) - 1u)) + 1;
+#if HDT_COLORS_HOIST
+        // Experimental (default off): the next node's pointer load is issued here, next to the colour-tree
+        // load below, instead of after the colour-tree checks and the sibling loop: two waits per level instead of three.
+        const u32 nextHandle = dag.child(handle, childOff);
+#endif
 
         if (level - 1 < colorTreeLevels) {
             colorNodeIndex = __ldg(col.nodes + colorNodeIndex + child);
@@ -222,7 +231,11 @@ __device__ u32 color_pixel(const DAG& dag, const ColorsDev& col, const u32 level
                     const uint2 l = dag.leaf(dag.child(handle, k++));
                     nofLeaves += __popc(l.x) + __popc(l.y);
                 }
+#if HDT_COLORS_HOIST
+            const uint2 l = dag.leaf(nextHandle);
+#else
             const uint2 l = dag.leaf(dag.child(handle, childOff));
+#endif
             const u32 bit = ((px & 1) ? 4 : 0) | ((py & 1) ? 2 : 0) | ((pz & 1) ? 1 : 0) | ((px & 2) ? 32 : 0) | ((py & 2) ? 16 : 0) | ((pz & 2) ? 8 : 0);
             const u64 l64 = (u64(l.y) << 32) | l.x;
             nofLeaves += __popcll(l64 & ((u64(1) << bit) - 1));
@@ -237,7 +250,11 @@ __device__ u32 color_pixel(const DAG& dag, const ColorsDev& col, const u32 level
                     nofLeaves += (!hashColors && level < col.topLevels) ? __ldg(col.enclosedLeaves + upper) : u64(upper);
                 }
         }
+#if HDT_COLORS_HOIST
+        handle = nextHandle;
+#else
         handle = dag.child(handle, childOff);
+#endif
     }
 
     if (col.kind == HDT_COLORS_UNCOMPRESSED) {

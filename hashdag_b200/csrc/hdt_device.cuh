@@ -16,6 +16,9 @@ using u16 = uint16_t;
 using u32 = uint32_t;
 using u64 = uint64_t;
 
+#ifndef HDT_LEAF_LATE
+#define HDT_LEAF_LATE 0
+#endif
 constexpr u32 kMaxLevels = 24;   // float node centres stay exact below 2^24
 constexpr u32 kPageWords = 512;  // C_pageSize, hash_dag_globals.h:10
 
@@ -295,6 +298,33 @@ struct Walker {
         // the arithmetic.  (With `cm = header & 0xFF` the AND sat right behind the LDG in the SASS and the warp stalled
         // there, in front of the arithmetic.)  Users of cm: popc(cm & (bit - 1)) with bit <= 0x80, and the stack push,
         // which masks it.
+#if HDT_LEAF_LATE
+        // Experimental (default off): the same treatment for the 64-bit leaf.  The leaf's first reader becomes
+        // `leaf & expand(mask)`, which needs the finished mask; the reduction to an 8-bit child mask follows.  cm of a
+        // leaf-level node is never read again (its children are bits of `leaf`, no pointer arithmetic), so it is set to vm.
+        bool fresh = false;
+        if (level <= leafLevel) {
+            const u32 next = dag.child(handle, __popc(cm & (__float_as_uint(st.w) - 1u)) + 1);
+            if (level < leafLevel) {
+                handle = next;
+                cm = dag.header(next);
+            } else {
+                leaf = dag.leaf(next);
+                fresh = true;
+            }
+        } else {
+            cm = second_child_mask(leaf, child);
+        }
+        const u32 hitMask = intersection_mask<false, TAME>(cx, cy, cz, radius, ray);
+        if (fresh) {
+            const u32 lo = (((hitMask & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu, hi = ((((hitMask >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            vm = first_child_mask(make_uint2(leaf.x & lo, leaf.y & hi));
+            cm = vm;
+        } else {
+            vm = cm & hitMask & 0xFF;
+        }
+        return 0;
+#else
         if (level <= leafLevel) {
             const u32 next = dag.child(handle, __popc(cm & (__float_as_uint(st.w) - 1u)) + 1);
             if (level < leafLevel) {
@@ -309,6 +339,7 @@ struct Walker {
         }
         vm = cm & intersection_mask<false, TAME>(cx, cy, cz, radius, ray) & 0xFF;
         return 0;
+#endif
     }
     // voxel coordinates once step() returned 1: centre = corner + 0.5
     __device__ __forceinline__ void voxel(u32& x, u32& y, u32& z) const { x = __float2uint_rz(cx); y = __float2uint_rz(cy); z = __float2uint_rz(cz); }

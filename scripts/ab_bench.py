@@ -1,4 +1,4 @@
-"""A/B timing of library builds: HDT_LIB=<path> [HDT_PERSISTENT=n] python scripts/ab_bench.py [F] [poses]"""
+"""A/B timing of library builds: HDT_LIB=<path> [AB_RESOLVED=0] [AB_CHECK=0] python scripts/ab_bench.py [F] [poses]"""
 import os, sys, time, json
 sys.path.insert(0, '.')
 import numpy as np
@@ -14,6 +14,9 @@ out = {"lib": os.path.basename(tracer.LIB_PATH), "persistent": os.environ.get("H
 for kind in ("hash", "basic"):
     if kind == "hash":
         dag, col = tracer.HashDAG.from_scene(scene), tracer.HashDAGColors.from_scene(scene)
+        if os.environ.get("AB_RESOLVED", "1") != "0":      # the shipped configuration: resolved pool (hdt_hash_dag_resolve)
+            dag = t.resolve_hash_dag(dag)
+            t.sync()
     else:
         dag, col = tracer.BasicDAG.from_scene(scene), tracer.BasicDAGCompressedColors.from_scene(scene)
     for p in poses[:4]:
