@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--cpu-sample-poses", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's own CUDA kernels (oracle/_ref) run after the timed region at N = 1")
     ap.add_argument("--dag", default="hash", choices=["hash", "basic"])
     ap.add_argument("--no-beam-prefetch", action="store_true", help="keep the beam kernels of frame n+1 behind all of frame n")
     ap.add_argument("--no-resolved", action="store_true", help="trace the HashDAG through its page table (A/B); default: the resolved pool (hdt_hash_dag_resolve)")
@@ -155,6 +156,8 @@ def run_reference_cpu(args):
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
         "dtype": "f32+f64+u32", "data": "synthetic",
         "config": workload_config(args, scene, W, H, args.gpus),
+        "implementation": {"what": "oracle/hdo_oracle.cpp: the reference's traversal restated for host cores (tracer.cu:7-697), rows of the image over threads",
+                           "threads": cores, "frame": [w, h], "rays_per_frame_fraction": (w * h) / (W * H)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -170,10 +173,34 @@ def workload_config(args, scene, W, H, world):
         "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, " + ("NCCL gather to rank 0" if getattr(args, "exchange", "peer") == "nccl" else "tiles stored into rank 0's frame over NVLink peer memory"),
         "l2_policy": "inputs larger than L2: each step is a different camera pose over a DAG pool >> 126 MB",
         "shadow_bias": 1.0, "fog_density": 0.0,
+        "scene_generator": "hashdag_b200/scene/scene_builder.cpp: seeded value-noise terrain + spheres (NOT the reference's FastNoise, src/FastNoise.cpp; "
+                           "no scene file of the reference is available offline)",
+    }
+
+
+def product_implementation(args, world):
+    """How OUR arm renders the workload (the reference arms describe themselves in their own `implementation`)."""
+    hashed = getattr(args, "dag", "hash") == "hash"
+    resolved = hashed and not getattr(args, "no_resolved", False)
+    return {
         "beam_prefetch": not getattr(args, "no_beam_prefetch", False),
-        "hash_dag_pointers": "resolved pool (child pointers pre-translated once, hdt_hash_dag_resolve)" if (getattr(args, "dag", "hash") == "hash" and not getattr(args, "no_resolved", False)) else "as stored",
+        "hash_dag_pointers": "resolved pool + prefix pool (hdt_hash_dag_resolve: child pointers pre-translated, sibling voxel counts pre-summed)" if resolved else "as stored",
+        "colors": "from the ancestor records of the paths pass (HDT_OPT_COLORS_RECORDED)" if resolved and os.environ.get("HDT_COLORS_RECORDED", "1") != "0" else "full DAG walk",
         "frames_in_flight": 2 if world > 1 else getattr(args, "frames_in_flight", 1),
     }
+
+
+def time_reference_kernels(rt, poses, info, step_ids, warmup_ids, dk, ck):
+    """The reference's three synchronous calls per frame (dag_tracer.cu:116-219), timed by its own cudaEvents (:130-138)."""
+    for i in warmup_ids:
+        rt.resolve_paths(dk, poses[i], info); rt.resolve_colors(dk, ck); rt.resolve_shadows(dk, poses[i], info, 1.0, 0.0)
+    tp = tc = ts = 0.0
+    for i in step_ids:
+        tp += rt.resolve_paths(dk, poses[i], info)
+        tc += rt.resolve_colors(dk, ck)
+        ts += rt.resolve_shadows(dk, poses[i], info, 1.0, 0.0)
+    n = max(1, len(step_ids))
+    return {"paths": tp / n, "colors": tc / n, "shadows": ts / n}
 
 
 def run_reference_cuda(args):
@@ -207,6 +234,7 @@ def run_reference_cuda(args):
         "impl": "reference-cuda", "metric": METRIC, "value": rays / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "dtype": "f32+f64+u32", "data": "synthetic",
         "config": workload_config(args, scene, W, H, 1),
+        "implementation": {"what": "oracle/_ref: the unmodified reference kernels (tracer.cu, dag_tracer.cu) compiled for sm_100a, three synchronous calls per frame"},
         "passes_ms": {"paths": tp / args.steps, "colors": tc / args.steps, "shadows": ts / args.steps},
         "mrays_s_paths_shadows_only": rays / ((tp + ts) * 1e-3) / 1e6,
         "note": "kernel times from the reference's own cudaEvents (dag_tracer.cu:130-138), summed; each call is synchronous",
@@ -464,6 +492,28 @@ def run_ours(args):
 
     sync_all()
     arm_fused(False)    # the pass timings below render frames that are not exchanged
+
+    # ---- N > 1: the SAME workload (same resolution, same poses) on ONE GPU, so that the scaling efficiency compares like
+    # with like.  Rank 0 renders whole frames on three contexts, exactly as a 1-GPU run of this resolution would; the other
+    # ranks wait at the barrier.
+    single_ms = None
+    if world > 1 and not os.environ.get("HDT_BENCH_NO_SINGLE"):
+        if rank == 0:
+            wl = [tracer.DAGTracer(True, W, H, args.levels, device=local_rank) for _ in range(3)]
+            for t_ in wl:
+                t_.set_option(tracer.OPT_BEAM_PREFETCH, 0 if args.no_beam_prefetch else 1)
+            for i in range(args.warmup):
+                wl[i % 3].enqueue_frame(params[i % len(params)], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+            for t_ in wl:
+                t_.sync()
+            for t_ in wl:
+                t_.timer_begin()
+            for i in range(args.steps):
+                wl[i % 3].enqueue_frame(params[(args.warmup + i) % len(params)], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+            single_ms = max(t_.timer_end() for t_ in wl) / args.steps
+            for t_ in wl:
+                t_.close()
+        barrier()
     # ---- per-pass kernel times on the sample poses (for the roofline) ------------------------
     sample_ids = [int(k * len(poses) / max(1, args.cpu_sample_poses)) for k in range(args.cpu_sample_poses)]
     pass_ms = {i: [0.0, 0.0, 0.0] for i in sample_ids}
@@ -522,6 +572,7 @@ def run_ours(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f32+f64+u32", "data": "synthetic",
         "config": workload_config(args, scene, W, H, world),
+        "implementation": product_implementation(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 96, "d2h_bytes_per_step": W * H * 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
@@ -533,6 +584,13 @@ def run_ours(args):
     }
     if exchange_mismatch is not None:
         out["parity_check_mismatched_pixels_vs_whole_frame_on_rank0"] = exchange_mismatch
+    if single_ms:
+        single_value = rays / (single_ms * 1e-3 * args.steps) / 1e6
+        out["single_gpu_same_workload"] = {"ms_per_step": single_ms, "value": single_value, "unit": UNIT, "frames_in_flight": 3,
+                                           "what": f"the same {W}x{H} frames rendered whole on rank 0's GPU alone (three contexts in flight, as `bench.py --gpus 1 "
+                                                   f"--width {W} --height {H}` does), measured in this run after the timed region"}
+        out["strong_scaling_efficiency"] = value / (world * single_value)
+        out["e2e_strong_scaling_efficiency"] = e2e_value / (world * single_value)
 
     # ---- CPU baseline + algorithmic bytes (bounded sample), roofline -------------------------
     if world == 1 and not args.no_cpu_baseline:
@@ -577,6 +635,63 @@ def run_ours(args):
                            "avg_launch_ms": gpu_ms_pass[dominant] / len(sample_ids),
                            "per_pass": {k: {"ms": gpu_ms_pass[k] / len(sample_ids), "algorithmic_GBps": ach[k],
                                             "bytes_per_launch": bytes_pass[k] / len(sample_ids)} for k in bytes_pass}}
+    # ---- the north star's anchor: the reference's own CUDA kernels on this GPU, scene and camera path ----------------
+    if world == 1 and not args.no_ref_cuda:
+        from oracle import ref
+        if ref.available(args.levels, W, H):
+            step_ids = [(args.warmup + i) % len(poses) for i in range(args.steps)]
+            warm_ids = [i % len(poses) for i in range(min(args.warmup, 3))]
+            # ours, synchronous: one frame at a time, nothing else in flight -- (a) the whole-frame call (one synchronisation per
+            # frame), (b) the three calls of the reference's interface, each synchronous like the reference's
+            for t_ in lanes:
+                t_.sync()
+            for i in warm_ids:
+                tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
+            fp = [0.0, 0.0, 0.0]
+            t0 = time.perf_counter()
+            for i in step_ids:
+                ms = tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
+                fp = [a + b for a, b in zip(fp, ms)]
+            frame_wall_ms = (time.perf_counter() - t0) * 1e3 / len(step_ids)
+            sp = [0.0, 0.0, 0.0]
+            for i in step_ids:
+                sp[0] += tr.resolve_paths(poses[i], info, dag)
+                sp[1] += tr.resolve_colors(dag, colors)
+                sp[2] += tr.resolve_shadows(poses[i], info, dag, 1.0, 0.0)
+            n = len(step_ids)
+            ours_frame = {k: v / n for k, v in zip(("paths", "colors", "shadows"), fp)}
+            ours_calls = {k: v / n for k, v in zip(("paths", "colors", "shadows"), sp)}
+            ours_img = {}
+            for i in sample_ids[:2]:
+                tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, host_frame)
+                ours_img[i] = host_frame.numpy().view(np.uint32).reshape(H, W).copy()
+            rt = ref.RefTracer(args.levels, W, H)
+            rt.load_scene(scene)
+            dk, ck = (1, 3) if hashed else (0, 1)
+            ref_ms = time_reference_kernels(rt, poses, info, step_ids, warm_ids, dk, ck)
+            ref_bad = 0
+            for i in sample_ids[:2]:
+                rt.resolve_paths(dk, poses[i], info); rt.resolve_colors(dk, ck); rt.resolve_shadows(dk, poses[i], info, 1.0, 0.0)
+                ref_bad += int((rt.read_colors() != ours_img[i]).sum())
+            rt.close()
+            ref_total = sum(ref_ms.values())
+            out["ref_cuda"] = {"what": "oracle/_ref: the UNMODIFIED reference kernels (tracer.cu:145-697 via dag_tracer.cu:116-219) compiled for sm_100a, same GPU, "
+                                       "DAG and the same K poses, after the timed region; kernel times from the reference's own cudaEvents, three synchronous calls per frame",
+                               "ms_per_step": ref_total, "passes_ms": ref_ms, "value": rays / (ref_total * 1e-3 * args.steps) / 1e6, "unit": UNIT}
+            out["ours_synchronous"] = {"three_calls_ms": ours_calls, "three_calls_ms_per_step": sum(ours_calls.values()),
+                                       "frame_call_ms": ours_frame, "frame_call_ms_per_step": sum(ours_frame.values()),
+                                       "frame_call_wall_ms_per_step": frame_wall_ms,
+                                       "note": "three_calls = hdt_resolve_paths / _colors / _shadows, each synchronous like DAGTracer::resolve_*; frame_call = hdt_resolve_frame "
+                                               "(the same three passes, one synchronisation, the shadow pass' set-up and beams beside the colours kernel)"}
+            out["vs_ref_cuda"] = {"pipelined": ref_total / (elapsed_ms / args.steps), "e2e": ref_total / (e2e_ms / args.steps),
+                                  "synchronous": ref_total / sum(ours_calls.values()), "synchronous_frame_call": ref_total / sum(ours_frame.values()),
+                                  "per_pass": {k: ref_ms[k] / ours_calls[k] for k in ref_ms},
+                                  "note": "reference ms / ours ms on the same frames; pipelined = K frames enqueued on "
+                                          f"{len(lanes)} contexts (the headline `value`), synchronous = one call at a time like the reference"}
+            out["parity_check_mismatched_pixels_vs_reference_kernels"] = ref_bad
+        else:
+            out["ref_cuda"] = {"unavailable": f"oracle/_ref has no build for depth {args.levels} at {W}x{H} (oracle/build_ref.py)"}
+
     if world > 1 and not args.no_cpu_baseline:
         # roofline of one rank's launch: the frame's algorithmic bytes (oracle access counts on rank 0's host cores) / N,
         # over the slowest rank's pass time

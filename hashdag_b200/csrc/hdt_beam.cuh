@@ -233,15 +233,20 @@ __device__ __forceinline__ void beam_traverse(const DAG& dag, const u32 levels, 
             radius = ra;
             level = nl;
         }
-        const u32 child = ORDERED ? u32(tab.child[(order << 8) | vm]) : (31 - __clz(vm));
-        const float4 st = tab.step[child];
+        const u32 child = ORDERED ? u32(tab.o[order].child[vm]) : (31 - __clz(vm));
+        const float4 st = tab.o[0].step[child];
         vm &= ~__float_as_uint(st.w);
-        if (vm) { stack[level] = make_uint2(handle, cm | (vm << 8)); pending |= 1u << level; }
+        if (ORDERED || vm) stack[level] = make_uint2(handle, cm | (vm << 8));   // ORDERED: every ancestor, like Walker::step
+        if (vm) pending |= 1u << level;
         radius = __fmul_rn(radius, 0.5f);
         cx = __fmaf_rn(st.x, radius, cx); cy = __fmaf_rn(st.y, radius, cy); cz = __fmaf_rn(st.z, radius, cz);
         ++level;
         if (level == levels) {
             out->level = __float2uint_rz(cx); out->pending = __float2uint_rz(cy); out->handle = __float2uint_rz(cz);
+            if (ORDERED) {   // the ancestors trace_paths hands on to trace_colors (ancestor_words)
+                out->leaf = leaf;
+                for (u32 l = kColorTreeDepth; l + 3 <= levels; ++l) out->stack[l] = stack[l];
+            }
             publish(kBeamHit);
             return;
         }
@@ -264,7 +269,9 @@ __device__ __forceinline__ void beam_traverse(const DAG& dag, const u32 levels, 
     }
     out->level = level; out->pending = pending; out->handle = handle;
     out->cm = cm; out->radius = radius; out->cx = cx; out->cy = cy; out->cz = cz; out->leaf = leaf;
-    for (u32 m = pending; m; m &= m - 1) {
+    // the pending entries; for primary rays also every ancestor below the colour tree (pending or not)
+    const u32 keep = ORDERED ? (pending | (((1u << level) - 1u) & ~((1u << kColorTreeDepth) - 1u))) : pending;
+    for (u32 m = keep; m; m &= m - 1) {
         const u32 l = __ffs(m) - 1;
         out->stack[l] = stack[l];
     }
@@ -282,13 +289,11 @@ __device__ __forceinline__ u32 beam_status(const BeamState* __restrict__ bs, con
     return word & 3u;
 }
 
-// Per-ray side: continue from a BeamState (status == kBeamResume).  The ray is tame by construction.
+// Per-ray side: load a BeamState (status == kBeamResume) into a walker; walk() (hdt_device.cuh) carries on from there.
+// The ray is tame by construction.
 template <class DAG, bool ORDERED>
-__device__ __forceinline__ bool traverse_from(const DAG& dag, const u32 levels, const Ray& ray, const TraverseTables& tab, const u32 order,
-                                              const BeamState* __restrict__ bs, u32& outx, u32& outy, u32& outz)
+__device__ __forceinline__ void resume_from(Walker<DAG>& w, WalkStack& stack, const Ray& ray, const BeamState* __restrict__ bs)
 {
-    Walker<DAG> w;
-    WalkStack stack;
     // written by a concurrently running kernel: read through L2 (ld.cg), never the non-coherent path
     const uint4 h0 = __ldcg(reinterpret_cast<const uint4*>(bs));
     const uint4 h1 = __ldcg(reinterpret_cast<const uint4*>(bs) + 1);
@@ -296,16 +301,12 @@ __device__ __forceinline__ bool traverse_from(const DAG& dag, const u32 levels, 
     w.level = h0.y; w.pending = h0.z; w.handle = h0.w;
     w.cm = h1.x; w.radius = __uint_as_float(h1.y); w.cx = __uint_as_float(h1.z); w.cy = __uint_as_float(h1.w);
     w.cz = __uint_as_float(h2.x); w.leaf = make_uint2(h2.z, h2.w);
-    for (u32 m = w.pending; m; m &= m - 1) {
+    const u32 keep = ORDERED ? (w.pending | (((1u << w.level) - 1u) & ~((1u << kColorTreeDepth) - 1u))) : w.pending;
+    for (u32 m = keep; m; m &= m - 1) {
         const u32 l = __ffs(m) - 1;
         stack[l] = __ldcg(&bs->stack[l]);
     }
     w.vm = w.cm & intersection_mask<false, true>(w.cx, w.cy, w.cz, w.radius, ray);
-    for (;;) {
-        const int r = w.template step<ORDERED, true>(dag, levels, ray, tab, order, stack);
-        if (r == 1) { w.voxel(outx, outy, outz); return true; }
-        if (r == 2) { outx = outy = outz = 0; return false; }
-    }
 }
 
 }  // namespace hdt

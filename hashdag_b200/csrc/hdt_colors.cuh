@@ -123,6 +123,55 @@ __device__ __forceinline__ CompressedColorDev leaf_get_color(const ColorLeafDev&
     return out;
 }
 
+// The same block as leaf_get_color finds, with a shorter chain of dependent loads: the reference's binary search
+// (vwsc.h:354-369) ends on the LAST block of the macro block whose first colour is <= local (blocks are sorted by their
+// first colour, and a macro block's first block starts at colour 0) after ~log2(n) dependent 8-byte loads -- about ten for
+// the ~1000 blocks per macro block of a noisy leaf.  Here every round probes K-1 evenly spaced headers at once
+// (independent loads, one latency) and keeps the K-th of the range that contains the answer: log_K(n) rounds.
+#ifndef HDT_COLOR_SEARCH_K
+#define HDT_COLOR_SEARCH_K 8
+#endif
+__device__ __forceinline__ CompressedColorDev leaf_get_color_wide(const ColorLeafDev& l, u64 colorIndex)
+{
+    constexpr u32 K = HDT_COLOR_SEARCH_K;
+    if (l.is_shared()) colorIndex += l.offset;
+    const u32 local = u32(colorIndex % kColorsPerMacroBlock);
+    const u32 macro = u32(colorIndex / kColorsPerMacroBlock);
+    const u64 bitBase = __ldg(l.macroBlocks + 2 * macro + 1);      // issued with the two range loads; used after the search
+    u32 lo = u32(__ldg(l.macroBlocks + 2 * macro));
+    u32 hi = (2 * (u64(macro) + 1) < l.nMacroWords) ? u32(__ldg(l.macroBlocks + 2 * (macro + 1)) - 1) : u32(l.nBlocks - 1);
+    const u32* hdrs = reinterpret_cast<const u32*>(l.blocks);      // low word of block i = hdrs[2 i]: weight offset | bpw-1 | first colour
+    // invariant: the answer lies in [lo, hi]
+    while (hi > lo) {
+        const u32 n = hi - lo + 1;                                  // >= 2
+        const u32 step = (n + K - 1) / K;                           // >= 1; probes at lo + i*step, i = 1 .. K-1, while <= hi
+        u32 first[K - 1];
+#pragma unroll
+        for (u32 i = 1; i < K; ++i) {
+            const u32 pos = lo + i * step;
+            first[i - 1] = pos <= hi ? (__ldg(hdrs + 2 * u64(pos)) & 0x3FFFu) : 0xFFFFFFFFu;
+        }
+        u32 j = 0;                                                  // probes whose block starts at or before `local` (a prefix of them)
+#pragma unroll
+        for (u32 i = 1; i < K; ++i) j += first[i - 1] <= local ? 1u : 0u;
+        lo += j * step;
+        hi = min(hi, lo + step - 1);
+    }
+    const u64 block = __ldg(l.blocks + lo);
+    const u32 hdr = u32(block);
+    CompressedColorDev out;
+    out.colorBits = u32(block >> 32);
+    out.weight = 0;
+    out.bitsPerWeight = ((hdr >> 16) == 0xFFFF) ? 0u : (((hdr >> 14) & 0x3) + 1);
+    if (out.bitsPerWeight) {
+        const u64 bitPtr = bitBase + (hdr >> 16) + u64(local - (hdr & 0x3FFF)) * out.bitsPerWeight;
+        const u8* bytes = reinterpret_cast<const u8*>(l.weights) + (bitPtr >> 3);
+        const u32 be16 = (u32(__ldg(bytes)) << 8) | u32(__ldg(bytes + 1));
+        out.weight = (be16 >> (16 - out.bitsPerWeight - u32(bitPtr & 7))) & ((1u << out.bitsPerWeight) - 1);
+    }
+    return out;
+}
+
 __device__ __forceinline__ u32 murmurhash32(u32 h)   // utils.h:68-76
 {
     h ^= h >> 16; h *= 0x85ebca6b; h ^= h >> 13; h *= 0xc2b2ae35; h ^= h >> 16;
@@ -152,24 +201,52 @@ struct ColorsParams {
     int debugColors; u32 debugIndexLevel; int overlay; hdt_tool_info tool;
 };
 
-// One pixel of tracer.cu:254-451.
-template <class DAG>
-__device__ u32 color_pixel(const DAG& dag, const ColorsDev& col, const u32 levels, const ColorsParams& prm, u32 px, u32 py, u32 pz)
-{
-    if ((px | py | pz) == 0) return float3_to_rgb888(__fdiv_rn(187.f, 255.f), __fdiv_rn(242.f, 255.f), __fdiv_rn(250.f, 255.f));
-    const float strength = prm.overlay ? tool_strength(prm.tool, px, py, pz) : 0.f;
-    auto set = [&](u32 color) {
+// Where a pixel's colour goes: the tool overlay of tracer.cu:276-286 and the "invalid" checkerboard of :288-292.
+struct ColorSink {
+    const ColorsParams& prm;
+    u32 px, py, pz;
+    float strength;
+    __device__ __forceinline__ ColorSink(const ColorsParams& p, u32 x, u32 y, u32 z) : prm(p), px(x), py(y), pz(z), strength(p.overlay ? tool_strength(p.tool, x, y, z) : 0.f) {}
+    __device__ __forceinline__ u32 set(u32 color) const
+    {
         if (prm.overlay && strength > 0.f) {
             const float3 c = rgb888_to_float3(color);
             const float f = clampf(100.f * strength, 0.f, .5f), g = 1.f - f;
             color = float3_to_rgb888(c.x * g + 1.f * f, c.y * g + 0.f * f, c.z * g + 0.f * f);
         }
         return color;
-    };
-    auto invalid = [&]() {
+    }
+    __device__ __forceinline__ u32 invalid() const
+    {
         const u32 b = (px ^ py ^ pz) & 1;
         return set(float3_to_rgb888(1.f, __uint2float_rn(b), 1.f - __uint2float_rn(b)));
-    };
+    }
+};
+
+__device__ __forceinline__ u32 sky_color() { return float3_to_rgb888(__fdiv_rn(187.f, 255.f), __fdiv_rn(242.f, 255.f), __fdiv_rn(250.f, 255.f)); }
+
+// The end of tracer.cu:254-451 for compressed colours: colour `nofLeaves` of `leaf`, through the debug views.
+template <bool WIDE>
+__device__ __forceinline__ u32 compressed_color(const ColorLeafDev& leaf, u64 nofLeaves, int dbg, const ColorSink& sink)
+{
+    const CompressedColorDev cc = WIDE ? leaf_get_color_wide(leaf, nofLeaves) : leaf_get_color(leaf, nofLeaves);
+    u32 color;
+    if (dbg == HDT_DEBUG_COLOR_BITS) color = 0;   // debug hash is compiled out in the BENCHMARK configuration (vwsc.h:96-104)
+    else if (dbg == HDT_DEBUG_MIN_COLOR) { const float3 c = rgb565_to_float3(cc.colorBits & 0xFFFF); color = float3_to_rgb888(c.x, c.y, c.z); }
+    else if (dbg == HDT_DEBUG_MAX_COLOR) { const float3 c = rgb565_to_float3(cc.colorBits >> 16); color = float3_to_rgb888(c.x, c.y, c.z); }
+    else if (dbg == HDT_DEBUG_WEIGHT) { const float w = color_weight(cc); color = float3_to_rgb888(w, w, w); }
+    else { const float3 c = color_value(cc); color = float3_to_rgb888(c.x, c.y, c.z); }
+    return sink.set(color);
+}
+
+// One pixel of tracer.cu:254-451.
+template <class DAG>
+__device__ u32 color_pixel(const DAG& dag, const ColorsDev& col, const u32 levels, const ColorsParams& prm, u32 px, u32 py, u32 pz)
+{
+    if ((px | py | pz) == 0) return sky_color();
+    const ColorSink sink(prm, px, py, pz);
+    auto set = [&](u32 color) { return sink.set(color); };
+    auto invalid = [&]() { return sink.invalid(); };
     const u32 leafLevel = levels - 2;
     const bool hashColors = col.kind == HDT_COLORS_HASH;
     const u32 colorTreeLevels = hashColors ? kColorTreeLevels : 0;
@@ -276,14 +353,48 @@ __device__ u32 color_pixel(const DAG& dag, const ColorsDev& col, const u32 level
         const float3 c = rgb888_to_float3(float3_to_rgb888(v, v, v));
         return set(float3_to_rgb888(c.x, c.y, c.z));
     }
-    const CompressedColorDev cc = leaf_get_color(leaf, nofLeaves);
-    u32 color;
-    if (dbg == HDT_DEBUG_COLOR_BITS) color = 0;   // debug hash is compiled out in the BENCHMARK configuration (vwsc.h:96-104)
-    else if (dbg == HDT_DEBUG_MIN_COLOR) { const float3 c = rgb565_to_float3(cc.colorBits & 0xFFFF); color = float3_to_rgb888(c.x, c.y, c.z); }
-    else if (dbg == HDT_DEBUG_MAX_COLOR) { const float3 c = rgb565_to_float3(cc.colorBits >> 16); color = float3_to_rgb888(c.x, c.y, c.z); }
-    else if (dbg == HDT_DEBUG_WEIGHT) { const float w = color_weight(cc); color = float3_to_rgb888(w, w, w); }
-    else { const float3 c = color_value(cc); color = float3_to_rgb888(c.x, c.y, c.z); }
-    return set(color);
+    return compressed_color<false>(leaf, nofLeaves, dbg, sink);
+}
+
+// The same pixel for a HashDAG with HashDAGColors when trace_paths left an AncestorRecord (hdt_device.cuh) and the
+// resolved pool has a prefix pool (hdt_resolve.cuh).  What is left of the reference's walk:
+//   * the ten levels of the colour tree (hash_dag_colors.h:33-50), a chain of dependent loads that needs only the path;
+//   * below the tree the voxel's index inside its colour leaf = sum over the ancestors of depth 10 .. levels-3 of the
+//     voxels under their earlier children -- ONE prefix-pool load per level at the recorded pointer word, all independent of
+//     each other and of the colour-tree chain -- plus the set bits below the voxel's own bit in its 64-bit leaf (recorded);
+//   * the colour decode, with the wide block search.
+// No DAG node is visited: the existence checks of tracer.cu:316-320 cannot fail for a path trace_paths has just walked
+// through this DAG (the launch code only takes this route for the DAG the paths frame was traced in).
+// Debug views that show node indices or positions take color_pixel.
+__device__ __forceinline__ u32 color_pixel_recorded(const u32* __restrict__ prefix, const ColorsDev& col, const u32 levels, const ColorsParams& prm,
+                                                    const u32 px, const u32 py, const u32 pz, const uint4 a, const uint4 b)
+{
+    const ColorSink sink(prm, px, py, pz);
+    // below the colour tree: independent loads, issued first
+    const u32 w[kMaxAncestorWords] = { a.x, a.y, a.z, a.w, b.x, b.y };
+    u32 below[kMaxAncestorWords];
+#pragma unroll
+    for (u32 i = 0; i < kMaxAncestorWords; ++i) below[i] = (kColorTreeDepth + i + 3 <= levels) ? __ldg(prefix + w[i]) : 0u;
+    // the colour tree
+    u32 colorNodeIndex = 0;
+#pragma unroll 1
+    for (u32 level = 1; level <= kColorTreeLevels; ++level) {
+        const u32 sh = levels - level;
+        const u32 child = (((px >> sh) & 1) << 2) | (((py >> sh) & 1) << 1) | ((pz >> sh) & 1);
+        colorNodeIndex = __ldg(col.nodes + colorNodeIndex + child);
+        if (level < kColorTreeLevels && !colorNodeIndex) return sink.invalid();
+    }
+    ColorLeafDev leaf;
+    if (colorNodeIndex & 0x80000000u) leaf = leaf_from_pod(col.leaves[colorNodeIndex & 0x7FFFFFFFu]);
+    else { leaf = col.leaf; leaf.offset = __ldg(col.offsets + colorNodeIndex); }
+    u64 nofLeaves = 0;
+#pragma unroll
+    for (u32 i = 0; i < kMaxAncestorWords; ++i) nofLeaves += below[i];
+    const u32 bit = ((px & 1) ? 4 : 0) | ((py & 1) ? 2 : 0) | ((pz & 1) ? 1 : 0) | ((px & 2) ? 32 : 0) | ((py & 2) ? 16 : 0) | ((pz & 2) ? 8 : 0);
+    const u64 l64 = (u64(b.w) << 32) | b.z;
+    nofLeaves += __popcll(l64 & ((u64(1) << bit) - 1));
+    if (!leaf.is_valid() || !leaf.is_valid_index(nofLeaves)) return sink.invalid();
+    return compressed_color<true>(leaf, nofLeaves, prm.debugColors, sink);
 }
 
 }  // namespace hdt

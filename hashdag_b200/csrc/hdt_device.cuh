@@ -49,9 +49,10 @@ struct BasicDagDev {
     __device__ __forceinline__ u32 root() const { return 0; }
     __device__ __forceinline__ u32 raw_root() const { return 0; }
     __device__ __forceinline__ u32 header(u32 h) const { return __ldg(data + h); }
-    __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(data + h + off); }
+    // h + off is formed in 32 bits (a node lies inside an array of < 2^32 words): one IMAD.WIDE instead of a 64-bit add chain
+    __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(data + u32(h + off)); }
     __device__ __forceinline__ u32 to_handle(u32 ptr) const { return ptr; }
-    __device__ __forceinline__ u32 child(u32 h, u32 off) const { return __ldg(data + h + off); }
+    __device__ __forceinline__ u32 child(u32 h, u32 off) const { return __ldg(data + u32(h + off)); }
     __device__ __forceinline__ uint2 leaf(u32 h) const { return make_uint2(__ldg(data + h), __ldg(data + h + 1)); }
 };
 
@@ -63,8 +64,8 @@ struct HashDagDev {
     __device__ __forceinline__ u32 root() const { return to_handle(firstNodeIndex); }
     __device__ __forceinline__ u32 raw_root() const { return firstNodeIndex; }
     __device__ __forceinline__ u32 header(u32 h) const { return __ldg(pool + h); }
-    __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(pool + h + off); }
-    __device__ __forceinline__ u32 child(u32 h, u32 off) const { return to_handle(__ldg(pool + h + off)); }
+    __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(pool + u32(h + off)); }
+    __device__ __forceinline__ u32 child(u32 h, u32 off) const { return to_handle(__ldg(pool + u32(h + off))); }
     // leaves sit at even bucket positions in 512-word pages: 8-byte aligned (hash_table.h:367-392)
     __device__ __forceinline__ uint2 leaf(u32 h) const { return __ldg(reinterpret_cast<const uint2*>(pool + h)); }
 };
@@ -78,22 +79,26 @@ struct HashDagResolvedDev {
     const u32* __restrict__ pool;        // resolved copy
     const u32* __restrict__ vpool;       // the caller's pool (virtual child pointers)
     const u32* __restrict__ pageTable;
+    const u32* __restrict__ prefix;      // optional: per child-pointer word, the voxels under the node's earlier children (hdt_resolve.cuh)
     u32 firstNodeIndex;
     __device__ __forceinline__ u32 to_handle(u32 vptr) const { return __ldg(pageTable + (vptr >> 9)) * kPageWords + (vptr & (kPageWords - 1)); }
     __device__ __forceinline__ u32 root() const { return to_handle(firstNodeIndex); }
     __device__ __forceinline__ u32 raw_root() const { return firstNodeIndex; }
     __device__ __forceinline__ u32 header(u32 h) const { return __ldg(pool + h); }
-    __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(vpool + h + off); }
-    __device__ __forceinline__ u32 child(u32 h, u32 off) const { return __ldg(pool + h + off); }
+    __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(vpool + u32(h + off)); }
+    __device__ __forceinline__ u32 child(u32 h, u32 off) const { return __ldg(pool + u32(h + off)); }
     __device__ __forceinline__ uint2 leaf(u32 h) const { return __ldg(reinterpret_cast<const uint2*>(pool + h)); }
 };
 
 // base_dag.h:16-58
+// Bit k of the result = byte k of the 64-bit leaf is non-zero.  Per word: the carry of (byte & 0x7F) + 0x7F ORed with the
+// byte's own top bit marks a non-zero byte at bit 7 of the byte; the multiplication gathers bits 7/15/23/31 into bits
+// 28..31 (no two partial products meet above bit 23).
 __device__ __forceinline__ u32 first_child_mask(uint2 leaf)
 {
-    u32 a = leaf.x | (leaf.x >> 4); a |= a >> 2; a |= a >> 1; a &= 0x01010101u;
-    u32 b = leaf.y | (leaf.y >> 4); b |= b >> 2; b |= b >> 1; b &= 0x01010101u;
-    return ((a * 0x01020408u) >> 24) | (((b * 0x01020408u) >> 24) << 4);
+    const u32 a = (((leaf.x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | leaf.x) & 0x80808080u;
+    const u32 b = (((leaf.y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | leaf.y) & 0x80808080u;
+    return ((a * 0x00204081u) >> 28) | (((b * 0x00204081u) >> 24) & 0xF0u);
 }
 __device__ __forceinline__ u32 second_child_mask(uint2 leaf, u32 firstChild)
 {
@@ -101,6 +106,9 @@ __device__ __forceinline__ u32 second_child_mask(uint2 leaf, u32 firstChild)
 }
 
 struct Ray { float ox, oy, oz, dx, dy, dz, ix, iy, iz; };
+
+// index of the highest set bit (x != 0): one FLO instead of the 31 - clz(x) pair
+__device__ __forceinline__ u32 top_bit(u32 x) { u32 r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }
 
 // Comparison -> all-ones / zero word (one FSET instead of FSETP + SEL).  Ordered compares: false
 // on NaN, like the C++ comparisons of the reference.
@@ -189,35 +197,38 @@ __device__ __forceinline__ u32 intersection_mask(float cx, float cy, float cz, f
     return mask;
 }
 
-// Shared-memory tables, filled once per CTA:
-//   child[order*256 + mask] = next_child(order, mask) (tracer.cu:7-17): first set bit of mask in the
-//                             order child ^ order, child = 0..7;
-//   step[c]                 = (+-1, +-1, +-1, 1<<c): direction of child c's centre from its parent's
-//                             (child bit 4 -> x, 2 -> y, 1 -> z, path.h:20-28) and its mask bit.
+// Shared-memory tables, filled once per CTA.  One 384-byte block per ray order (tracer.cu:7-17: children are visited in
+// the order child ^ order, child = 0..7):
+//   o[order].child[mask] = next_child(order, mask): first set bit of mask in that order;
+//   o[order].step[c]     = (+-1, +-1, +-1, 1<<c): direction of child c's centre from its parent's (child bit 4 -> x,
+//                          2 -> y, 1 -> z, path.h:20-28) and its mask bit (the same in every block).
+// A ray keeps ONE register -- the shared-memory address of its block -- and reaches both tables from it with immediate
+// offsets (table_child / table_step below).
 struct TraverseTables {
-    float4 step[8];
-    u8 child[8 * 256];
+    struct Block { u8 child[256]; float4 step[8]; } o[8];
 };
 
+static_assert(sizeof(TraverseTables::Block) == 384 && sizeof(TraverseTables) == 3072, "table layout is addressed by hand");
 static_assert(sizeof(TraverseTables) % 16 == 0, "copied as uint4");
 
-// Host-side initialisation (once per context); CTAs copy the 2176 bytes with 16-byte loads.
+// Host-side initialisation (once per context); CTAs copy the table with 16-byte loads.
 inline void build_tables(TraverseTables& t)
 {
-    for (u32 i = 0; i < 8 * 256; ++i) {
-        const u32 order = i >> 8, mask = i & 255;
-        u32 res = 0;
-        for (int child = 7; child >= 0; --child) {
-            const u32 c = u32(child) ^ order;
-            if (mask & (1u << c)) res = c;
+    for (u32 order = 0; order < 8; ++order) {
+        for (u32 mask = 0; mask < 256; ++mask) {
+            u32 res = 0;
+            for (int child = 7; child >= 0; --child) {
+                const u32 c = u32(child) ^ order;
+                if (mask & (1u << c)) res = c;
+            }
+            t.o[order].child[mask] = u8(res);
         }
-        t.child[i] = u8(res);
-    }
-    for (u32 c = 0; c < 8; ++c) {
-        const u32 bit = 1u << c;
-        float w;
-        memcpy(&w, &bit, 4);
-        t.step[c] = make_float4((c & 4) ? 1.f : -1.f, (c & 2) ? 1.f : -1.f, (c & 1) ? 1.f : -1.f, w);
+        for (u32 c = 0; c < 8; ++c) {
+            const u32 bit = 1u << c;
+            float w;
+            memcpy(&w, &bit, 4);
+            t.o[order].step[c] = make_float4((c & 4) ? 1.f : -1.f, (c & 2) ? 1.f : -1.f, (c & 1) ? 1.f : -1.f, w);
+        }
     }
 }
 
@@ -226,6 +237,27 @@ __device__ __forceinline__ void load_tables(TraverseTables& dst, const TraverseT
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(&dst);
     for (u32 i = threadIdx.x; i < sizeof(TraverseTables) / 16; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+// Shared-window address of the block of ray order `order`.  The empty asm keeps the compiler from re-deriving the
+// address from the ray's direction signs inside the traversal loop (it did: 8 instructions per node visit).
+__device__ __forceinline__ u32 table_block(const TraverseTables& tab, u32 order)
+{
+    u32 a = u32(__cvta_generic_to_shared(&tab)) + order * u32(sizeof(TraverseTables::Block));
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ u32 table_child(u32 block, u32 mask)
+{
+    u32 c;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(block + mask));
+    return c;
+}
+__device__ __forceinline__ float4 table_step(u32 block, u32 child)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+256];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(block + child * 16u));
+    return v;
 }
 
 // Stack DFS shared by trace_paths (ORDERED: children in ray order, first voxel wins,
@@ -263,13 +295,16 @@ struct Walker {
 
     // One descent (preceded by an ascent if the current node is exhausted).
     // Returns 0: keep going, 1: reached a voxel (cx,cy,cz = its centre), 2: left the DAG.
+    // `block`: the ray's table block (table_block).  ORDERED walks store every level's entry, pending or not: when the
+    // walk ends on a voxel, stack[d] holds the handle and child mask of the voxel's ancestor of every depth d, which
+    // trace_paths hands to trace_colors (ancestor_words below).
     template <bool ORDERED, bool TAME>
-    __device__ __forceinline__ int step(const DAG& dag, const u32 levels, const Ray& ray, const TraverseTables& tab, const u32 order, WalkStack& stack)
+    __device__ __forceinline__ int step(const DAG& dag, const u32 levels, const Ray& ray, const u32 block, WalkStack& stack)
     {
         const u32 leafLevel = levels - 2;
         if (vm == 0) {
             if (pending == 0) return 2;
-            const u32 nl = 31 - __clz(pending);
+            const u32 nl = top_bit(pending);
             pending ^= 1u << nl;
             const uint2 e = stack[nl];
             handle = e.x; cm = e.y & 0xFF; vm = e.y >> 8;
@@ -284,10 +319,11 @@ struct Walker {
             radius = ra;
             level = nl;
         }
-        const u32 child = ORDERED ? u32(tab.child[(order << 8) | vm]) : (31 - __clz(vm));
-        const float4 st = tab.step[child];
+        const u32 child = ORDERED ? table_child(block, vm) : top_bit(vm);
+        const float4 st = table_step(block, child);
         vm &= ~__float_as_uint(st.w);
-        if (vm) { stack[level] = make_uint2(handle, (cm & 0xFF) | (vm << 8)); pending |= 1u << level; }
+        if (ORDERED || vm) stack[level] = make_uint2(handle, (cm & 0xFF) | (vm << 8));
+        if (vm) pending |= 1u << level;
         radius = __fmul_rn(radius, 0.5f);
         cx = __fmaf_rn(st.x, radius, cx); cy = __fmaf_rn(st.y, radius, cy); cz = __fmaf_rn(st.z, radius, cz);
         ++level;
@@ -345,18 +381,45 @@ struct Walker {
     __device__ __forceinline__ void voxel(u32& x, u32& y, u32& z) const { x = __float2uint_rz(cx); y = __float2uint_rz(cy); z = __float2uint_rz(cz); }
 };
 
+// Finish a walk that has been started (Walker::start) or resumed (traverse_from, hdt_beam.cuh).
 template <class DAG, bool ORDERED, bool TAME>
-__device__ __forceinline__ bool traverse(const DAG& dag, const u32 levels, const Ray& ray, const TraverseTables& tab, const u32 order,
-                                         u32& outx, u32& outy, u32& outz)
+__device__ __forceinline__ bool walk(Walker<DAG>& w, WalkStack& stack, const DAG& dag, const u32 levels, const Ray& ray, const u32 block,
+                                     u32& outx, u32& outy, u32& outz)
 {
-    Walker<DAG> w;
-    WalkStack stack;
-    w.template start<TAME>(dag, levels, ray);
     for (;;) {
-        const int r = w.template step<ORDERED, TAME>(dag, levels, ray, tab, order, stack);
+        const int r = w.template step<ORDERED, TAME>(dag, levels, ray, block, stack);
         if (r == 1) { w.voxel(outx, outy, outz); return true; }
         if (r == 2) { outx = outy = outz = 0; return false; }
     }
+}
+
+// What trace_paths leaves for trace_colors about a hit voxel (x, y, z): for every ancestor of depth d in [10, levels-3] --
+// the DAG levels below the colour tree (hash_dag_globals.h:7), whose earlier siblings trace_colors has to count
+// (tracer.cu:391-420) -- the physical index of the child-pointer word the path follows out of that ancestor, and the 64-bit
+// leaf the voxel lies in.  `entry(d)` returns the walk's stack entry of depth d (handle, childMask | ...).
+constexpr u32 kColorTreeDepth = 10;   // C_colorTreeLevels
+constexpr u32 kMaxAncestorWords = 6;  // depths 10 .. 15: DAGs of up to 18 levels
+struct AncestorRecord { uint4 a, b; };   // a = words of depths 10..13, b = { depth 14, depth 15, leaf.x, leaf.y }
+
+template <class Entry>
+__device__ __forceinline__ AncestorRecord ancestor_words(const u32 levels, const u32 x, const u32 y, const u32 z, const uint2 leaf, Entry entry)
+{
+    u32 w[kMaxAncestorWords];
+#pragma unroll
+    for (u32 i = 0; i < kMaxAncestorWords; ++i) {
+        const u32 d = kColorTreeDepth + i;
+        w[i] = 0;
+        if (d + 3 <= levels) {
+            const uint2 e = entry(d);
+            const u32 sh = levels - 1 - d;
+            const u32 child = (((x >> sh) & 1) << 2) | (((y >> sh) & 1) << 1) | ((z >> sh) & 1);
+            w[i] = e.x + 1 + __popc(e.y & 0xFFu & ((1u << child) - 1u));
+        }
+    }
+    AncestorRecord r;
+    r.a = make_uint4(w[0], w[1], w[2], w[3]);
+    r.b = make_uint4(w[4], w[5], leaf.x, leaf.y);
+    return r;
 }
 
 

@@ -22,14 +22,20 @@ struct ExchangeCounters { u32 arrivals; u32 credit; u32 pad[62]; };   // 256 B, 
 
 __device__ __forceinline__ u32 load_volatile(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
 
-// One thread: wait until *counter - target >= 0 (wrap-safe).  Gives up after ~2 s of GPU time and raises *timedOut
-// (host-mapped), so a lost peer shows up as an error instead of a hung box.
-__global__ void exchange_wait_kernel(const u32* counter, u32 target, u32* timedOut)
+// One thread: wait until *counter - target >= 0 (wrap-safe).  After maxCycles SM cycles (0 = wait for ever; default
+// ~20 s, HDT_OPT_EXCHANGE_TIMEOUT_MS) it gives up: *timedOut (host-mapped) is raised, so a lost peer shows up as an error
+// at the next host-synchronising call instead of a hung box, and *abortFlag (device) makes the kernels queued behind it
+// skip their stores and signals -- a frame that timed out is dropped, never half-written over one still being read.
+__global__ void exchange_wait_kernel(const u32* counter, u32 target, unsigned long long maxCycles, u32* timedOut, u32* abortFlag)
 {
     const long long t0 = clock64();
     while (int(load_volatile(counter) - target) < 0) {
         __nanosleep(100);
-        if (clock64() - t0 > 4000000000ll) { *reinterpret_cast<volatile u32*>(timedOut) = 1; break; }
+        if (maxCycles && (unsigned long long)(clock64() - t0) > maxCycles) {
+            *reinterpret_cast<volatile u32*>(timedOut) = 1;
+            *reinterpret_cast<volatile u32*>(abortFlag) = 1;
+            break;
+        }
     }
     __threadfence_system();
 }
@@ -40,8 +46,9 @@ __global__ void exchange_publish_kernel(u32* counter, u32 value)
     *reinterpret_cast<volatile u32*>(counter) = value;
 }
 
-__global__ void exchange_signal_kernel(u32* arrivals)   // a rank that owns no tile still has to arrive
+__global__ void exchange_signal_kernel(u32* arrivals, const u32* abortFlag)   // a rank that owns no tile still has to arrive
 {
+    if (load_volatile(abortFlag)) return;
     __threadfence_system();
     atomicAdd_system(arrivals, 1u);
 }
@@ -65,8 +72,9 @@ __device__ __forceinline__ void exchange_signal_last_cta(u32* __restrict__ ctasD
 // This rank's compact tiles (each (1<<tileLog2)^2 pixels, row-major, owned tiles back to back) -> the row-major frame,
 // which may live in another GPU's memory.  One CTA per 16 tile rows; the last CTA to finish signals `arrivals`.
 __global__ void __launch_bounds__(256) exchange_scatter_kernel(const u32* __restrict__ compact, u32* __restrict__ frame, const PixelMap map,
-                                                                u32* __restrict__ ctasDone, u32* arrivals)
+                                                                u32* __restrict__ ctasDone, u32* arrivals, const u32* abortFlag)
 {
+    if (load_volatile(abortFlag)) return;             // the wait in front of this launch gave up: drop the frame
     const u32 T = 1u << map.tileLog2, rowsPerCta = 16, ctasPerTile = T / rowsPerCta;
     const u32 slot = blockIdx.x / ctasPerTile, row0 = (blockIdx.x % ctasPerTile) * rowsPerCta;
     const u32 t = map.rank + slot * map.world;

@@ -22,7 +22,7 @@ using namespace hdt;
 
 static_assert(sizeof(hdt_basic_dag) == 16, "BasicDAG layout");
 static_assert(sizeof(hdt_hash_dag) == 32, "HashDAG layout");
-static_assert(sizeof(hdt_resolved_hash_dag) == 40, "hdt_resolved_hash_dag layout");
+static_assert(sizeof(hdt_resolved_hash_dag) == 48, "hdt_resolved_hash_dag layout");
 static_assert(sizeof(hdt_color_leaf) == 104, "CompressedColorLeaf layout");
 static_assert(sizeof(hdt_basic_compressed_colors) == 128, "BasicDAGCompressedColors layout");
 static_assert(sizeof(hdt_basic_uncompressed_colors) == 40, "BasicDAGUncompressedColors layout");
@@ -48,6 +48,9 @@ namespace {
 #endif
 #ifndef HDT_MIN_BLOCKS_COLORS
 #define HDT_MIN_BLOCKS_COLORS 16
+#endif
+#ifndef HDT_MIN_BLOCKS_COLORS_RECORDED
+#define HDT_MIN_BLOCKS_COLORS_RECORDED 16
 #endif
 constexpr u32 kBlockW = HDT_BLOCK_W, kBlockH = HDT_BLOCK_H, kWarpsX = kBlockW / 8;
 constexpr u32 kBlockThreads = kBlockW * kBlockH;
@@ -132,14 +135,18 @@ __global__ void __launch_bounds__(32) beam_paths_kernel(const CameraParams cam, 
 #pragma unroll
     for (int k = 0; k < 3; ++k) br.o[k] = { cam.camf[k], cam.camf[k] };
     if (!s0.w || !finish_beam(br)) { store_release(&out->status, (tag << 2) | kBeamNone); return; }
-    beam_traverse<DAG, true>(dag, levels, br, tab, s1.w, maxVisits, tag, out);
+    beam_traverse<DAG, true>(dag, levels, br, tab, s1.w & 7u, maxVisits, tag, out);
 }
+
+// Where trace_paths leaves the ancestor records of hit pixels for trace_colors (two planes indexed like the paths buffer;
+// null = not wanted).
+struct AncestorPlanes { uint4* __restrict__ a; uint4* __restrict__ b; };
 
 template <class DAG>
 __global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_paths_kernel(const CameraParams cam, const DAG dag, const u32 levels, const PixelMap map,
                                                                     const RayPlanes dirs, uint4* __restrict__ paths,
                                                                     const TraverseTables* __restrict__ tables, const BeamState* __restrict__ beams,
-                                                                    const u32 tag)
+                                                                    const u32 tag, const AncestorPlanes anc)
 {
     __shared__ TraverseTables tab;
     load_tables(tab, tables);
@@ -154,17 +161,37 @@ __global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_paths_ker
     const u64 idx = map.index(x, y);
 
     u32 px, py, pz;
-    if (status == kBeamHit) { px = __ldcg(&bs->level); py = __ldcg(&bs->pending); pz = __ldcg(&bs->handle); }
+    if (status == kBeamHit) {
+        px = __ldcg(&bs->level); py = __ldcg(&bs->pending); pz = __ldcg(&bs->handle);
+        if (anc.a && (px | py | pz)) {
+            const AncestorRecord r = ancestor_words(levels, px, py, pz, __ldcg(&bs->leaf), [&](u32 d) { return __ldcg(&bs->stack[d]); });
+            anc.a[idx] = r.a; anc.b[idx] = r.b;
+        }
+    }
     else if (status == kBeamMiss) px = py = pz = 0;
     else {
         Ray ray;
         ray.ox = cam.camf[0]; ray.oy = cam.camf[1]; ray.oz = cam.camf[2];
         dirs.load(idx, ray.dx, ray.dy, ray.dz);
         ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
-        const u32 order = ray_order(ray);
-        if (status == kBeamResume) traverse_from<DAG, true>(dag, levels, ray, tab, order, bs, px, py, pz);
-        else if (ray_is_tame(ray)) traverse<DAG, true, true>(dag, levels, ray, tab, order, px, py, pz);
-        else traverse<DAG, true, false>(dag, levels, ray, tab, order, px, py, pz);
+        const u32 block = table_block(tab, ray_order(ray));
+        Walker<DAG> w;
+        WalkStack stack;
+        bool hit;
+        if (status == kBeamResume) {
+            resume_from<DAG, true>(w, stack, ray, bs);
+            hit = walk<DAG, true, true>(w, stack, dag, levels, ray, block, px, py, pz);
+        } else if (ray_is_tame(ray)) {
+            w.template start<true>(dag, levels, ray);
+            hit = walk<DAG, true, true>(w, stack, dag, levels, ray, block, px, py, pz);
+        } else {
+            w.template start<false>(dag, levels, ray);
+            hit = walk<DAG, true, false>(w, stack, dag, levels, ray, block, px, py, pz);
+        }
+        if (anc.a && hit && (px | py | pz)) {
+            const AncestorRecord r = ancestor_words(levels, px, py, pz, w.leaf, [&](u32 d) { return stack[d]; });
+            anc.a[idx] = r.a; anc.b[idx] = r.b;
+        }
     }
     paths[idx] = make_uint4(px, py, pz, 0);
 }
@@ -181,6 +208,19 @@ __global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS_COLORS) trace_co
     const u64 idx = map.index(x, y);
     const uint4 p = paths[idx];
     out[idx] = color_pixel(dag, colors, levels, prm, p.x, p.y, p.z);
+}
+
+// trace_colors from the ancestor records of the paths pass (color_pixel_recorded, hdt_colors.cuh).
+__global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS_COLORS_RECORDED) trace_colors_recorded_kernel(const u32* __restrict__ prefix, const ColorsDev colors, const u32 levels,
+                                                                     const ColorsParams prm, const PixelMap map, const uint4* __restrict__ paths,
+                                                                     const uint4* __restrict__ ancA, const uint4* __restrict__ ancB, u32* __restrict__ out)
+{
+    u32 x, y;
+    if (!thread_pixel(map, x, y)) return;
+    const u64 idx = map.index(x, y);
+    const uint4 p = paths[idx];
+    if ((p.x | p.y | p.z) == 0) { out[idx] = sky_color(); return; }
+    out[idx] = color_pixel_recorded(prefix, colors, levels, prm, p.x, p.y, p.z, __ldg(ancA + idx), __ldg(ancB + idx));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -309,9 +349,19 @@ __device__ __forceinline__ void shadow_pixel(const CameraParams& cam, const Shad
         ray.dx = sp.sunX; ray.dy = sp.sunY; ray.dz = sp.sunZ;
         ray.ix = __frcp_rn(ray.dx); ray.iy = __frcp_rn(ray.dy); ray.iz = __frcp_rn(ray.dz);
         u32 hx, hy, hz;
-        if (status == kBeamResume) shadowed = traverse_from<DAG, false>(dag, levels, ray, tab, 0, bs, hx, hy, hz);
-        else shadowed = ray_is_tame(ray) ? traverse<DAG, false, true>(dag, levels, ray, tab, 0, hx, hy, hz)
-                                         : traverse<DAG, false, false>(dag, levels, ray, tab, 0, hx, hy, hz);
+        const u32 block = table_block(tab, 0);
+        Walker<DAG> w;
+        WalkStack stack;
+        if (status == kBeamResume) {
+            resume_from<DAG, false>(w, stack, ray, bs);
+            shadowed = walk<DAG, false, true>(w, stack, dag, levels, ray, block, hx, hy, hz);
+        } else if (ray_is_tame(ray)) {
+            w.template start<true>(dag, levels, ray);
+            shadowed = walk<DAG, false, true>(w, stack, dag, levels, ray, block, hx, hy, hz);
+        } else {
+            w.template start<false>(dag, levels, ray);
+            shadowed = walk<DAG, false, false>(w, stack, dag, levels, ray, block, hx, hy, hz);
+        }
     }
     shade(shadowed ? 0.5f : 1.0f, true);
 }
@@ -430,6 +480,7 @@ struct hdt_ctx {
     u32* frameColors = nullptr;
     u32* pathCache = nullptr;    // pinned, 4 words
     u64 launches = 0;
+    u64 recordedColorPasses = 0;   // colour passes that read the ancestor records instead of walking the DAG
     TraverseTables* tables = nullptr;   // device copy of the traversal tables
     // Beam pre-pass (hdt_beam.cuh): per pass (0 = paths, 1 = shadows) one BeamState + BeamSeed per 8x4-pixel
     // tile (= warp of the per-ray kernels) and three float planes of per-pixel ray data (directions / origins).
@@ -451,11 +502,18 @@ struct hdt_ctx {
     bool xFused = false;                // HDT_OPT_EXCHANGE_FUSED: shadow passes store into rank 0's frame themselves
     u32 xFusedSeq = 0;                  // sequence number the last fused shadow pass stored for
     u32* xTimedOutDev = nullptr;        // device alias of xTimedOut
-    u32* xCtasDone = nullptr;           // device, scatter kernel's last-CTA counter
+    u32* xCtasDone = nullptr;           // device, 2 words: the scatter kernel's last-CTA counter, the abort flag of a wait that gave up
+    unsigned long long xWaitCycles = 40000000000ull;   // ~20 s of SM clock; 0 = wait for ever (HDT_OPT_EXCHANGE_TIMEOUT_MS)
     u32* xTimedOut = nullptr;           // pinned + mapped: raised by a wait kernel that gave up
     char* stagingHost = nullptr;        // hdt_apply_ranges_host: pinned + device staging, bump-allocated, reset when full
     char* stagingDev = nullptr;
     size_t stagingCap = 0, stagingUsed = 0;
+    // Ancestor records of the last paths frame (AncestorRecord, hdt_device.cuh), written for HDT_DAG_HASH_RESOLVED DAGs with a
+    // prefix pool; ancFor* say which DAG that frame was traced in (trace_colors takes the short route only for the same one).
+    uint4* anc[2] = {};
+    bool useRecorded = true;            // HDT_OPT_COLORS_RECORDED
+    bool ancValid = false;
+    const u32* ancForPool = nullptr; const u32* ancForPrefix = nullptr; u32 ancForRoot = 0;
     u32* physToVirt = nullptr;          // hdt_hash_dag_resolve: physical page -> virtual page (grow-only)
     size_t physToVirtPages = 0;
     void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, per-macro-block sums (grow-only)
@@ -488,7 +546,9 @@ int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
         cudaFree(c->beams[i]); c->beams[i] = nullptr;
         cudaFree(c->seeds[i]); c->seeds[i] = nullptr;
         cudaFree(c->rays[i]); c->rays[i] = nullptr;
+        cudaFree(c->anc[i]); c->anc[i] = nullptr;
     }
+    c->ancValid = false;
     PixelMap& m = c->map;
     m.tileLog2 = tileLog2; m.world = world; m.rank = rank;
     const u32 T = 1u << tileLog2;
@@ -505,6 +565,9 @@ int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
         HDT_CUDA(cudaMalloc(&c->seeds[i], size_t(c->n_beams()) * sizeof(BeamSeed)));
         HDT_CUDA(cudaMalloc(&c->rays[i], n * 3 * sizeof(float)));
     }
+    // ancestor records: DAGs with HashDAGColors (levels - 2 > 10 colour-tree levels) of at most 18 levels
+    if (c->levels >= kColorTreeDepth + 3 && c->levels <= kColorTreeDepth + 2 + kMaxAncestorWords && n)
+        for (int i = 0; i < 2; ++i) HDT_CUDA(cudaMalloc(&c->anc[i], n * sizeof(uint4)));
     HDT_CUDA(cudaMemsetAsync(c->paths, 0, n * sizeof(uint4), c->stream));
     HDT_CUDA(cudaMemsetAsync(c->colors, 0, n * sizeof(u32), c->stream));
     HDT_CUDA(cudaStreamSynchronize(c->stream));
@@ -533,12 +596,13 @@ int parse_dag(int kind, const void* pod, size_t size, DagArg& out)
         return HDT_OK;
     }
     if (kind == HDT_DAG_HASH_RESOLVED) {
-        if (size != sizeof(hdt_resolved_hash_dag)) return fail(HDT_ERR_POD_SIZE, "hdt_resolved_hash_dag: expected 40 bytes");
+        if (size != sizeof(hdt_resolved_hash_dag)) return fail(HDT_ERR_POD_SIZE, "hdt_resolved_hash_dag: expected 48 bytes");
         hdt_resolved_hash_dag d; memcpy(&d, pod, sizeof(d));
         if (!d.dag.pool || !d.dag.page_table || !d.resolved_pool) return fail(HDT_ERR_ARG, "resolved HashDAG: null pool / page table / resolved pool");
         if (u64(d.dag.pool_top) * kPageWords > (u64(1) << 32)) return fail(HDT_ERR_ARG, "HashDAG: pool beyond 2^32 words");
         if ((d.dag.first_node_index >> 9) >= d.dag.page_table_size) return fail(HDT_ERR_ARG, "resolved HashDAG: root outside the page table");
         out.resolved.pool = d.resolved_pool; out.resolved.vpool = d.dag.pool; out.resolved.pageTable = d.dag.page_table;
+        out.resolved.prefix = d.prefix_pool;
         out.resolved.firstNodeIndex = d.dag.first_node_index;
         return HDT_OK;
     }
@@ -625,23 +689,29 @@ ShadowParams make_shadow(float bias, float fog)
 // Launch tags run through 0 .. 2^30-2; the state buffers are initialised with 2^30-1.
 u32 next_beam_tag(hdt_ctx* c) { return c->beamTag = (c->beamTag + 1) % 0x3FFFFFFFu; }
 
-void launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
+// Every launch helper returns HDT_OK or the code of the first failing CUDA call (named in hdt_last_error()).
+#define HDT_LAUNCHED(what)                                       \
+    do {                                                         \
+        cudaError_t e__ = cudaGetLastError();                    \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what);     \
+        ++c->launches;                                           \
+    } while (0)
+
+int launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
 {
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
-    if (!grid.x) return;
+    c->ancValid = false;
+    if (!grid.x) return HDT_OK;
     // Ray setup and beams on the side stream.  Normally they are ordered after everything enqueued on the
     // main stream so far.  With HDT_OPT_BEAM_PREFETCH the caller promises that the DAG is not modified by
     // work queued on the tracer's stream, and they only wait for the previous paths kernel (the last
     // reader of their buffers): enqueued right behind the previous frame, they then run beside its
     // colours / shadows kernels, and the per-ray kernel below finds every beam finished.
-    cudaEventRecord(c->fork[0], c->stream);
-    if (c->beamPrefetch) cudaStreamWaitEvent(c->side, c->traceDone[0], 0);
-    else {
-        cudaStreamWaitEvent(c->side, c->fork[0], 0);
-    }
+    HDT_CUDA(cudaEventRecord(c->fork[0], c->stream));
+    HDT_CUDA(cudaStreamWaitEvent(c->side, c->beamPrefetch ? c->traceDone[0] : c->fork[0], 0));
     setup_paths_kernel<<<grid, block, 0, c->side>>>(cam, c->map, c->ray_planes(0), c->seeds[0]);
-    cudaEventRecord(c->setupDone[0], c->side);
-    ++c->launches;
+    HDT_LAUNCHED("setup_paths_kernel");
+    HDT_CUDA(cudaEventRecord(c->setupDone[0], c->side));
     const BeamState* beams = nullptr;
     u32 tag = 0;
     if (c->useBeams) {
@@ -652,42 +722,64 @@ void launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
         if (d.kind == HDT_DAG_BASIC) beam_paths_kernel<BasicDagDev><<<g, b, 0, c->side>>>(cam, d.basic, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
         else if (d.kind == HDT_DAG_HASH) beam_paths_kernel<HashDagDev><<<g, b, 0, c->side>>>(cam, d.hash, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
         else beam_paths_kernel<HashDagResolvedDev><<<g, b, 0, c->side>>>(cam, d.resolved, c->levels, c->seeds[0], c->beams[0], nb, c->beamMaxVisits, tag, c->tables);
-        ++c->launches;
+        HDT_LAUNCHED("beam_paths_kernel");
         c->lastBeamPass = 0;
     }
-    cudaEventRecord(c->join[0], c->side);
-    cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[0] : c->setupDone[0], 0);   // the directions
-    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
-    else if (d.kind == HDT_DAG_HASH) trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
-    else trace_paths_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, d.resolved, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag);
-    cudaEventRecord(c->traceDone[0], c->stream);
-    ++c->launches;
-    cudaStreamWaitEvent(c->stream, c->join[0], 0);   // a synchronisation of the main stream covers the beam kernel too
+    HDT_CUDA(cudaEventRecord(c->join[0], c->side));
+    HDT_CUDA(cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[0] : c->setupDone[0], 0));   // the directions
+    // ancestor records for trace_colors: only a resolved HashDAG with a prefix pool can use them
+    AncestorPlanes anc{ nullptr, nullptr };
+    if (d.kind == HDT_DAG_HASH_RESOLVED && d.resolved.prefix && c->anc[0] && c->useRecorded) anc = AncestorPlanes{ c->anc[0], c->anc[1] };
+    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
+    else if (d.kind == HDT_DAG_HASH) trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
+    else trace_paths_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, d.resolved, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
+    HDT_LAUNCHED("trace_paths_kernel");
+    if (anc.a) { c->ancValid = true; c->ancForPool = d.resolved.pool; c->ancForPrefix = d.resolved.prefix; c->ancForRoot = d.resolved.firstNodeIndex; }
+    HDT_CUDA(cudaEventRecord(c->traceDone[0], c->stream));
+    HDT_CUDA(cudaStreamWaitEvent(c->stream, c->join[0], 0));   // a synchronisation of the main stream covers the beam kernel too
+    return HDT_OK;
 }
-void launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const ColorsParams& prm)
+
+// Can trace_colors take the short route (color_pixel_recorded)?  Only for the DAG the current paths frame was traced in
+// (same resolved pool, prefix pool and root: the records hold physical word indices of that pool), HashDAGColors, and a
+// view that decodes a colour (the index / position / colour-tree debug views show what only the full walk computes).
+bool colors_recorded_ok(const hdt_ctx* c, const DagArg& d, const ColorsDev& col, const ColorsParams& prm)
+{
+    return c->useRecorded && c->ancValid && d.kind == HDT_DAG_HASH_RESOLVED && d.resolved.pool == c->ancForPool && d.resolved.prefix &&
+           d.resolved.prefix == c->ancForPrefix && d.resolved.firstNodeIndex == c->ancForRoot && col.kind == HDT_COLORS_HASH &&
+           prm.debugColors != HDT_DEBUG_INDEX && prm.debugColors != HDT_DEBUG_POSITION && prm.debugColors != HDT_DEBUG_COLOR_TREE;
+}
+
+int launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const ColorsParams& prm)
 {
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
-    if (!grid.x) return;
-    if (d.kind == HDT_DAG_BASIC) trace_colors_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(d.basic, col, c->levels, prm, c->map, c->paths, c->colors);
+    if (!grid.x) return HDT_OK;
+    if (colors_recorded_ok(c, d, col, prm))
+    {
+        trace_colors_recorded_kernel<<<grid, block, 0, c->stream>>>(d.resolved.prefix, col, c->levels, prm, c->map, c->paths, c->anc[0], c->anc[1], c->colors);
+        ++c->recordedColorPasses;
+    }
+    else if (d.kind == HDT_DAG_BASIC) trace_colors_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(d.basic, col, c->levels, prm, c->map, c->paths, c->colors);
     else if (d.kind == HDT_DAG_HASH) trace_colors_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(d.hash, col, c->levels, prm, c->map, c->paths, c->colors);
     else trace_colors_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(d.resolved, col, c->levels, prm, c->map, c->paths, c->colors);
-    ++c->launches;
+    HDT_LAUNCHED("trace_colors_kernel");
+    return HDT_OK;
 }
 // trace_shadows in two halves so that a whole-frame call can enqueue the first one (ray setup + beams, which
 // only need the paths frame; side stream) before the colours kernel and the second one after it.
 struct ShadowPrep { const BeamState* beams = nullptr; u32 tag = 0; bool valid = false; };
 
-ShadowPrep prepare_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp)
+int prepare_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp, ShadowPrep& prep)
 {
-    ShadowPrep prep;
+    prep = ShadowPrep{};
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
-    if (!grid.x) return prep;
+    if (!grid.x) return HDT_OK;
     prep.valid = true;
-    cudaEventRecord(c->fork[1], c->stream);
-    cudaStreamWaitEvent(c->side, c->fork[1], 0);
+    HDT_CUDA(cudaEventRecord(c->fork[1], c->stream));
+    HDT_CUDA(cudaStreamWaitEvent(c->side, c->fork[1], 0));
     setup_shadows_kernel<<<grid, block, 0, c->side>>>(cam, sp, c->map, c->paths, c->ray_planes(1), c->seeds[1]);
-    cudaEventRecord(c->setupDone[1], c->side);
-    ++c->launches;
+    HDT_LAUNCHED("setup_shadows_kernel");
+    HDT_CUDA(cudaEventRecord(c->setupDone[1], c->side));
     if (c->useBeams) {
         prep.beams = c->beams[1];
         prep.tag = next_beam_tag(c);
@@ -696,25 +788,27 @@ ShadowPrep prepare_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam,
         if (d.kind == HDT_DAG_BASIC) beam_shadows_kernel<BasicDagDev><<<g, b, 0, c->side>>>(sp, d.basic, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
         else if (d.kind == HDT_DAG_HASH) beam_shadows_kernel<HashDagDev><<<g, b, 0, c->side>>>(sp, d.hash, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
         else beam_shadows_kernel<HashDagResolvedDev><<<g, b, 0, c->side>>>(sp, d.resolved, c->levels, c->seeds[1], c->beams[1], nb, c->beamMaxVisits, prep.tag, c->tables);
-        ++c->launches;
+        HDT_LAUNCHED("beam_shadows_kernel");
         c->lastBeamPass = 1;
     }
-    cudaEventRecord(c->join[1], c->side);
-    return prep;
+    HDT_CUDA(cudaEventRecord(c->join[1], c->side));
+    return HDT_OK;
 }
-void finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp, const ShadowPrep& prep)
+int finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp, const ShadowPrep& prep)
 {
-    if (!prep.valid) return;
+    if (!prep.valid) return HDT_OK;
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
-    cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[1] : c->setupDone[1], 0);   // the origins
+    HDT_CUDA(cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[1] : c->setupDone[1], 0));   // the origins
     // Fused framebuffer exchange: this pass writes the final colours, so it can store them into rank 0's frame itself.
     ExchangeOut xo{ nullptr, nullptr, nullptr };
     if (c->xFused && c->xBlock) {
+        if (c->xFusedSeq == c->xSeq + 1)
+            return fail(HDT_ERR_STATE, "fused framebuffer exchange: a second shadows pass before hdt_exchange_frame (every fused shadows pass must be followed by one)");
         const u32 seq = c->xSeq + 1;
         ExchangeCounters* k = reinterpret_cast<ExchangeCounters*>(reinterpret_cast<char*>(c->xBlock) + ((size_t(c->map.width) * c->map.height * 4 + 255) & ~size_t(255)));
         if (c->map.rank != 0) {   // rank 0 must have consumed the previous frame of this lane
-            exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, c->xTimedOutDev);
-            ++c->launches;
+            exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, c->xWaitCycles, c->xTimedOutDev, c->xCtasDone + 1);
+            HDT_LAUNCHED("exchange_wait_kernel");
         }
         xo = ExchangeOut{ c->xBlock, c->xCtasDone, c->map.rank != 0 ? &k->arrivals : nullptr };
         c->xFusedSeq = seq;
@@ -722,13 +816,16 @@ void finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const 
     if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
     else if (d.kind == HDT_DAG_HASH) trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
     else trace_shadows_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, sp, d.resolved, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
-    cudaEventRecord(c->traceDone[1], c->stream);
-    ++c->launches;
-    cudaStreamWaitEvent(c->stream, c->join[1], 0);
+    HDT_LAUNCHED("trace_shadows_kernel");
+    HDT_CUDA(cudaEventRecord(c->traceDone[1], c->stream));
+    HDT_CUDA(cudaStreamWaitEvent(c->stream, c->join[1], 0));
+    return HDT_OK;
 }
-void launch_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp)
+int launch_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const ShadowParams& sp)
 {
-    finish_shadows(c, d, cam, sp, prepare_shadows(c, d, cam, sp));
+    ShadowPrep prep;
+    if (int rc = prepare_shadows(c, d, cam, sp, prep)) return rc;
+    return finish_shadows(c, d, cam, sp, prep);
 }
 
 int check_combo(int dagKind, int colorsKind)
@@ -738,10 +835,22 @@ int check_combo(int dagKind, int colorsKind)
     return HDT_OK;
 }
 
+// After a host synchronisation: did a framebuffer-exchange wait give up since the last check?  (The stream is idle here.)
+int check_exchange(hdt_ctx* c)
+{
+    if (c->xTimedOut && *reinterpret_cast<volatile u32*>(c->xTimedOut)) {
+        *reinterpret_cast<volatile u32*>(c->xTimedOut) = 0;
+        if (c->xCtasDone) cudaMemsetAsync(c->xCtasDone, 0, 2 * sizeof(u32), c->stream);
+        return fail(HDT_ERR_STATE, "framebuffer exchange: a rank did not arrive (or rank 0 did not release) within the exchange timeout; the frame was dropped");
+    }
+    return HDT_OK;
+}
+
 int finish_timed(hdt_ctx* c, cudaEvent_t a, cudaEvent_t b, float* ms)
 {
     HDT_CUDA(cudaEventSynchronize(b));
     HDT_CUDA(cudaGetLastError());
+    if (int rc = check_exchange(c)) return rc;
     if (ms) HDT_CUDA(cudaEventElapsedTime(ms, a, b));
     return HDT_OK;
 }
@@ -753,6 +862,7 @@ extern "C" {
 const char* hdt_last_error(void) { return g_lastError.c_str(); }
 int hdt_version(void) { return 1; }
 uint64_t hdt_launch_count(const hdt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t hdt_recorded_color_passes(const hdt_ctx* ctx) { return ctx ? ctx->recordedColorPasses : 0; }
 
 int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt_ctx** out)
 {
@@ -767,6 +877,7 @@ int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt
     c->map.width = width; c->map.height = height;
     if (const char* env = getenv("HDT_BEAMS")) c->useBeams = atoi(env) != 0;
     if (const char* env = getenv("HDT_BEAM_PREFETCH")) c->beamPrefetch = atoi(env) != 0;
+    if (const char* env = getenv("HDT_COLORS_RECORDED")) c->useRecorded = atoi(env) != 0;
     if (const char* env = getenv("HDT_BEAM_MAX_VISITS")) c->beamMaxVisits = u32(atoi(env) > 0 ? atoi(env) : 1);
     cudaError_t e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking);
     c->stream = c->ownStream;
@@ -781,7 +892,7 @@ int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->setupDone[i]);
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->traceDone[i]);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&c->hitCounter, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->hitCounter, 8 * sizeof(unsigned long long));   // hit count / beam statistics
     if (e == cudaSuccess) e = cudaMallocHost(&c->pathCache, 4 * sizeof(u32));
     if (e != cudaSuccess) { hdt_destroy(c); return cuda_fail(e, "hdt_create"); }
     {
@@ -819,7 +930,7 @@ int hdt_destroy(hdt_ctx* c)
     cudaFree(c->stagingDev);
     if (c->side) cudaStreamSynchronize(c->side);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(c->beams[i]); cudaFree(c->seeds[i]); cudaFree(c->rays[i]);
+        cudaFree(c->beams[i]); cudaFree(c->seeds[i]); cudaFree(c->rays[i]); cudaFree(c->anc[i]);
         if (c->fork[i]) cudaEventDestroy(c->fork[i]);
         if (c->join[i]) cudaEventDestroy(c->join[i]);
         if (c->setupDone[i]) cudaEventDestroy(c->setupDone[i]);
@@ -838,6 +949,12 @@ int hdt_set_option(hdt_ctx* c, int option, int value)
     if (option == HDT_OPT_BEAM_PREFETCH) { c->beamPrefetch = value != 0; return HDT_OK; }
     if (option == HDT_OPT_BEAM_SERIAL) { c->beamSerial = value != 0; return HDT_OK; }
     if (option == HDT_OPT_EXCHANGE_FUSED) { c->xFused = value != 0; return HDT_OK; }
+    if (option == HDT_OPT_COLORS_RECORDED) { c->useRecorded = value != 0; c->ancValid = false; return HDT_OK; }
+    if (option == HDT_OPT_EXCHANGE_TIMEOUT_MS) {
+        if (value < 0) return fail(HDT_ERR_ARG, "exchange timeout must be >= 0 ms (0 = wait for ever)");
+        c->xWaitCycles = (unsigned long long)value * 2000000ull;   // SM clock <= 2 GHz: at least `value` ms
+        return HDT_OK;
+    }
     if (option == HDT_OPT_BEAM_MAX_VISITS) { if (value < 1) return fail(HDT_ERR_ARG, "beam visit cap must be >= 1"); c->beamMaxVisits = u32(value); return HDT_OK; }
     return fail(HDT_ERR_ARG, "unknown option");
 }
@@ -856,7 +973,7 @@ int hdt_resolve_paths(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_
     if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, d)) return rc;
     HDT_CUDA(cudaSetDevice(c->device));
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    launch_paths(c, d, make_cam(cam, ray_min, ray_ddx, ray_ddy));
+    if (int rc = launch_paths(c, d, make_cam(cam, ray_min, ray_ddx, ray_ddy))) return rc;
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     return finish_timed(c, c->ev[0], c->ev[1], ms);
 }
@@ -875,7 +992,7 @@ int hdt_resolve_colors(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag
     if (tool) prm.tool = *tool;
     HDT_CUDA(cudaSetDevice(c->device));
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    launch_colors(c, d, col, prm);
+    if (int rc = launch_colors(c, d, col, prm)) return rc;
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     return finish_timed(c, c->ev[0], c->ev[1], ms);
 }
@@ -888,7 +1005,7 @@ int hdt_resolve_shadows(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t da
     if (int rc = parse_dag(dag_kind, dag_pod, dag_pod_size, d)) return rc;
     HDT_CUDA(cudaSetDevice(c->device));
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    launch_shadows(c, d, make_cam(cam, ray_min, ray_ddx, ray_ddy), make_shadow(shadow_bias, fog_density));
+    if (int rc = launch_shadows(c, d, make_cam(cam, ray_min, ray_ddx, ray_ddy), make_shadow(shadow_bias, fog_density))) return rc;
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     return finish_timed(c, c->ev[0], c->ev[1], ms);
 }
@@ -907,15 +1024,15 @@ static int enqueue_frame(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t d
     ColorsParams prm{};
     HDT_CUDA(cudaSetDevice(c->device));
     if (events) HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    launch_paths(c, d, cp);
+    if (int rc = launch_paths(c, d, cp)) return rc;
     if (events) HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     // the shadow pass' ray setup and beams only need the paths frame: start them beside the colours kernel
     const ShadowParams sp = make_shadow(shadow_bias, fog_density);
     ShadowPrep prep;
-    if (with_shadows) prep = prepare_shadows(c, d, cp, sp);
-    launch_colors(c, d, col, prm);
+    if (with_shadows) if (int rc = prepare_shadows(c, d, cp, sp, prep)) return rc;
+    if (int rc = launch_colors(c, d, col, prm)) return rc;
     if (events) HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    if (with_shadows) finish_shadows(c, d, cp, sp, prep);
+    if (with_shadows) if (int rc = finish_shadows(c, d, cp, sp, prep)) return rc;
     if (events) HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
     if (host_colors)
         HDT_CUDA(cudaMemcpyAsync(host_colors, c->colors, u64(c->map.width) * c->map.height * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
@@ -930,6 +1047,7 @@ int hdt_resolve_frame(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_
                                shadow_bias, fog_density, with_shadows, host_colors, true)) return rc;
     HDT_CUDA(cudaStreamSynchronize(c->stream));
     HDT_CUDA(cudaGetLastError());
+    if (int rc = check_exchange(c)) return rc;
     if (ms) {
         HDT_CUDA(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
         HDT_CUDA(cudaEventElapsedTime(&ms[1], c->ev[1], c->ev[2]));
@@ -952,11 +1070,7 @@ int hdt_sync(hdt_ctx* c)
     HDT_CUDA(cudaSetDevice(c->device));
     HDT_CUDA(cudaStreamSynchronize(c->stream));
     HDT_CUDA(cudaGetLastError());
-    if (c->xTimedOut && *reinterpret_cast<volatile u32*>(c->xTimedOut)) {
-        *reinterpret_cast<volatile u32*>(c->xTimedOut) = 0;
-        return fail(HDT_ERR_STATE, "framebuffer exchange: a rank did not arrive (or rank 0 did not release) within ~2 s of GPU time");
-    }
-    return HDT_OK;
+    return check_exchange(c);
 }
 
 int hdt_timer_begin(hdt_ctx* c)
@@ -975,7 +1089,7 @@ int hdt_timer_end(hdt_ctx* c, float* ms)
     HDT_CUDA(cudaEventSynchronize(c->timer[1]));
     HDT_CUDA(cudaGetLastError());
     HDT_CUDA(cudaEventElapsedTime(ms, c->timer[0], c->timer[1]));
-    return HDT_OK;
+    return check_exchange(c);
 }
 
 int hdt_count_hits(hdt_ctx* c, uint64_t* n_hits)
@@ -1012,16 +1126,13 @@ int hdt_beam_stats(hdt_ctx* c, uint64_t out[5])
     const BeamState* beams = c->beams[c->lastBeamPass];
     if (!beams || !n) return HDT_OK;
     HDT_CUDA(cudaSetDevice(c->device));
-    unsigned long long* dev = nullptr;
-    HDT_CUDA(cudaMalloc(&dev, 5 * sizeof(unsigned long long)));
-    cudaMemsetAsync(dev, 0, 5 * sizeof(unsigned long long), c->stream);
+    unsigned long long* dev = c->hitCounter;   // 8 words of scratch
+    HDT_CUDA(cudaMemsetAsync(dev, 0, 5 * sizeof(unsigned long long), c->stream));
     beam_stats_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(beams, n, dev);
-    ++c->launches;
+    HDT_LAUNCHED("beam_stats_kernel");
     unsigned long long host[5] = {};
-    cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(dev);
-    if (e != cudaSuccess) return cuda_fail(e, "hdt_beam_stats");
+    HDT_CUDA(cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 5; ++i) out[i] = host[i];
     return HDT_OK;
 }
@@ -1060,7 +1171,7 @@ static int read_frame(hdt_ctx* c, bool paths, void* host)
         if (paths) HDT_CUDA(cudaMemcpyAsync(host, c->paths, n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
         else HDT_CUDA(cudaMemcpyAsync(host, c->colors, n * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
         HDT_CUDA(cudaStreamSynchronize(c->stream));
-        return HDT_OK;
+        return check_exchange(c);
     }
     const dim3 block(32, 8), grid((c->map.width + 31) / 32, (c->map.height + 7) / 8);
     if (paths) {
@@ -1077,7 +1188,7 @@ static int read_frame(hdt_ctx* c, bool paths, void* host)
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));
     HDT_CUDA(cudaGetLastError());
-    return HDT_OK;
+    return check_exchange(c);
 }
 
 int hdt_read_paths(hdt_ctx* c, uint32_t* host) { return read_frame(c, true, host); }
@@ -1137,8 +1248,8 @@ ExchangeCounters* exchange_counters(const hdt_ctx* c) { return reinterpret_cast<
 int exchange_common(hdt_ctx* c)
 {
     if (!c->xCtasDone) {
-        HDT_CUDA(cudaMalloc(&c->xCtasDone, sizeof(u32)));
-        HDT_CUDA(cudaMemset(c->xCtasDone, 0, sizeof(u32)));
+        HDT_CUDA(cudaMalloc(&c->xCtasDone, 2 * sizeof(u32)));
+        HDT_CUDA(cudaMemset(c->xCtasDone, 0, 2 * sizeof(u32)));
     }
     if (!c->xTimedOut) {
         HDT_CUDA(cudaHostAlloc(&c->xTimedOut, sizeof(u32), cudaHostAllocMapped));
@@ -1216,22 +1327,22 @@ int hdt_exchange_frame(hdt_ctx* c)
     const bool fused = c->xFusedSeq == seq && c->grid_blocks() > 0;   // the last shadow pass already stored (and signalled) this frame
     const u32 grid = fused ? 0 : c->nOwnedTiles * (T / 16);
     const bool root = c->map.rank == 0;
+    u32* abortDev = c->xCtasDone + 1;
     if (!root && !fused) {   // the root must have consumed the previous frame of this lane before it is overwritten
-        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, timedOutDev);
-        ++c->launches;
+        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, c->xWaitCycles, timedOutDev, abortDev);
+        HDT_LAUNCHED("exchange_wait_kernel");
     }
     if (grid) {
-        exchange_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->colors, c->xBlock, c->map, c->xCtasDone, root ? nullptr : &k->arrivals);
-        ++c->launches;
+        exchange_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->colors, c->xBlock, c->map, c->xCtasDone, root ? nullptr : &k->arrivals, abortDev);
+        HDT_LAUNCHED("exchange_scatter_kernel");
     } else if (!root && !fused) {
-        exchange_signal_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals);
-        ++c->launches;
+        exchange_signal_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals, abortDev);
+        HDT_LAUNCHED("exchange_signal_kernel");
     }
     if (root && c->map.world > 1) {
-        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals, (c->map.world - 1) * seq, timedOutDev);
-        ++c->launches;
+        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals, (c->map.world - 1) * seq, c->xWaitCycles, timedOutDev, abortDev);
+        HDT_LAUNCHED("exchange_wait_kernel");
     }
-    HDT_CUDA(cudaGetLastError());
     return HDT_OK;
 }
 
@@ -1282,7 +1393,7 @@ int hdt_apply_ranges_host(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload
     return HDT_OK;
 }
 
-int hdt_hash_dag_resolve(hdt_ctx* c, const hdt_hash_dag* dag, size_t dag_size, uint32_t* resolved_pool_dev, uint64_t capacity_words,
+int hdt_hash_dag_resolve(hdt_ctx* c, const hdt_hash_dag* dag, size_t dag_size, uint32_t* resolved_pool_dev, uint32_t* prefix_pool_dev, uint64_t capacity_words,
                          const hdt_range* ranges_host, uint32_t n_ranges)
 {
     if (!c || !dag || !resolved_pool_dev) return fail(HDT_ERR_ARG, "hdt_hash_dag_resolve: null argument");
@@ -1315,7 +1426,7 @@ int hdt_hash_dag_resolve(hdt_ctx* c, const hdt_hash_dag* dag, size_t dag_size, u
     }
     HDT_CUDA(cudaMemsetAsync(c->physToVirt, 0xFF, size_t(dag->pool_top) * sizeof(u32), c->stream));
     map_pages_kernel<<<(dag->page_table_size + 255) / 256, 256, 0, c->stream>>>(dag->page_table, dag->page_table_size, c->physToVirt, dag->pool_top);
-    ++c->launches;
+    HDT_LAUNCHED("map_pages_kernel");
     const u32* dPages = nullptr;
     u32 nPages = dag->pool_top;
     if (ranges_host) {
@@ -1340,9 +1451,9 @@ int hdt_hash_dag_resolve(hdt_ctx* c, const hdt_hash_dag* dag, size_t dag_size, u
         c->stagingUsed += need;
         nPages = u32(pages.size());
     }
-    resolve_pages_kernel<<<(nPages + 3) / 4, 128, 0, c->stream>>>(dag->pool, dag->page_table, c->physToVirt, dPages, nPages, HashLayoutDev{ c->levels }, resolved_pool_dev);
-    ++c->launches;
-    HDT_CUDA(cudaGetLastError());
+    resolve_pages_kernel<<<(nPages + 3) / 4, 128, 0, c->stream>>>(dag->pool, dag->page_table, c->physToVirt, dPages, nPages,
+                                                                  HashLayoutDev{ c->levels, dag->page_table_size, dag->pool_top }, resolved_pool_dev, prefix_pool_dev);
+    HDT_LAUNCHED("resolve_pages_kernel");
     return HDT_OK;
 }
 

@@ -280,12 +280,14 @@ class HashDagReplica:
         self.page_table = T._to_device(page_table, device)
         self.pool_top, self.first_node_index = int(pool_top), int(first_node_index)
         # the resolved pool (child pointers pre-translated, csrc/hdt_resolve.cuh) follows every edit page by page
-        self.resolved_pool = None
+        # ... and so does the prefix pool (voxels under a node's earlier children: trace_colors without the DAG walk)
+        self.resolved_pool = self.prefix_pool = None
         if resolved:
             self.resolved_pool = torch.zeros(cap, dtype=torch.int32, device=device)
+            self.prefix_pool = torch.zeros(cap, dtype=torch.int32, device=device)
             torch.cuda.synchronize()                    # the uploads above ran on torch's stream, the resolve runs on the tracer's
             self.levels = levels
-            tracer_obj.resolve_hash_dag(self._hash_dag(), self.resolved_pool)
+            tracer_obj.resolve_hash_dag(self._hash_dag(), self.resolved_pool, None, self.prefix_pool)
         self.has_colors = color_nodes is not None
         if self.has_colors:
             ncap = max(int(color_node_capacity), int(color_nodes.size))
@@ -309,7 +311,7 @@ class HashDagReplica:
         self.pool_top, self.first_node_index = int(delta.pool_top), int(delta.first_node_index)
         if self.resolved_pool is not None and len(delta.pool_ranges):
             # pages whose words changed, plus nothing else: older nodes never point at newer ones and their pointers stay valid
-            self.tracer.resolve_hash_dag(self._hash_dag(), self.resolved_pool, delta.pool_ranges)
+            self.tracer.resolve_hash_dag(self._hash_dag(), self.resolved_pool, delta.pool_ranges, self.prefix_pool)
         if self.has_colors and delta.n_color_nodes:
             if delta.n_color_nodes > self.color_nodes.numel():
                 grown = torch.zeros(2 * delta.n_color_nodes, dtype=torch.int32, device=self.device)
@@ -356,7 +358,7 @@ class HashDagReplica:
 
     def dag(self):
         d = self._hash_dag()
-        return d if self.resolved_pool is None else self._T.ResolvedHashDAG(d, self.resolved_pool)
+        return d if self.resolved_pool is None else self._T.ResolvedHashDAG(d, self.resolved_pool, self.prefix_pool)
 
     def colors(self):
         T = self._T

@@ -26,7 +26,7 @@ LIB_PATH = os.environ.get("HDT_LIB", os.path.join(_HERE, "libhashdag_b200.so")) 
 DAG_BASIC, DAG_HASH, DAG_HASH_RESOLVED = 0, 1, 2
 COLORS_UNCOMPRESSED, COLORS_COMPRESSED, COLORS_ERRORS, COLORS_HASH = 0, 1, 2, 3
 UNIQUE_OFFSET = 0xFFFFFFFFFFFFFFFF
-OPT_BEAMS, OPT_BEAM_MAX_VISITS, OPT_BEAM_PREFETCH, OPT_BEAM_SERIAL, OPT_EXCHANGE_FUSED = 1, 2, 3, 4, 5
+OPT_BEAMS, OPT_BEAM_MAX_VISITS, OPT_BEAM_PREFETCH, OPT_BEAM_SERIAL, OPT_EXCHANGE_FUSED, OPT_COLORS_RECORDED, OPT_EXCHANGE_TIMEOUT_MS = 1, 2, 3, 4, 5, 6, 7
 
 # EDebugColors, tracer.h:7-17
 DEBUG_NONE, DEBUG_INDEX, DEBUG_POSITION, DEBUG_COLOR_TREE, DEBUG_COLOR_BITS, DEBUG_MIN_COLOR, DEBUG_MAX_COLOR, DEBUG_WEIGHT = range(8)
@@ -36,7 +36,7 @@ EXPORTS = (
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
     "hdt_partition_buffers", "hdt_assemble_colors", "hdt_exchange_create", "hdt_exchange_open", "hdt_exchange_block", "hdt_exchange_attach",
-    "hdt_exchange_frame", "hdt_exchange_release", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_hash_dag_resolve", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_version",
+    "hdt_exchange_frame", "hdt_exchange_release", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_hash_dag_resolve", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_recorded_color_passes", "hdt_version",
 )
 ERR_CAPACITY = 4
 
@@ -95,7 +95,7 @@ def load_library():
     lib.hdt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.hdt_apply_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.hdt_apply_ranges_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
-    lib.hdt_hash_dag_resolve.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    lib.hdt_hash_dag_resolve.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     lib.hdt_rebuild_color_leaf.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                            C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), fp]
     u3 = C.POINTER(C.c_uint32)
@@ -103,6 +103,8 @@ def load_library():
     lib.hdt_is_empty.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_uint32, u3, u3, C.POINTER(C.c_int), fp]
     lib.hdt_launch_count.restype = C.c_uint64
     lib.hdt_launch_count.argtypes = [C.c_void_p]
+    lib.hdt_recorded_color_passes.restype = C.c_uint64
+    lib.hdt_recorded_color_passes.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -183,15 +185,16 @@ class HashDAG:
 
 
 class ResolvedHashDAG:
-    """A HashDAG + its resolved pool (hdt_resolved_hash_dag, 40 B): the copy of the pool in which every child pointer
-    already holds the child's physical word index (csrc/hdt_resolve.cuh).  Accepted wherever a HashDAG is; same frames."""
+    """A HashDAG + its resolved pool (hdt_resolved_hash_dag, 48 B): the copy of the pool in which every child pointer
+    already holds the child's physical word index, and optionally the prefix pool (voxels under a node's earlier children,
+    which lets trace_colors skip the DAG walk); csrc/hdt_resolve.cuh.  Accepted wherever a HashDAG is; same frames."""
     kind = DAG_HASH_RESOLVED
 
-    def __init__(self, dag: HashDAG, resolved_pool):
-        self.dag, self.resolved_pool, self.levels = dag, resolved_pool, dag.levels
+    def __init__(self, dag: HashDAG, resolved_pool, prefix_pool=None):
+        self.dag, self.resolved_pool, self.prefix_pool, self.levels = dag, resolved_pool, prefix_pool, dag.levels
 
     def pod(self) -> bytes:
-        return self.dag.pod() + struct.pack("<Q", _ptr(self.resolved_pool))
+        return self.dag.pod() + struct.pack("<QQ", _ptr(self.resolved_pool), _ptr(self.prefix_pool))
 
 
 class CompressedColorLeaf:
@@ -435,20 +438,22 @@ class DAGTracer:
         assert payload.dtype.itemsize == 4 and ranges.dtype.itemsize == 24
         _check(self._lib.hdt_apply_ranges_host(self._ctx, dst_tensor.data_ptr(), payload.ctypes.data, payload.size, ranges.ctypes.data, len(ranges)))
 
-    def resolve_hash_dag(self, dag: "HashDAG", resolved_pool=None, ranges: "np.ndarray | None" = None) -> "ResolvedHashDAG":
-        """hdt_hash_dag_resolve: fill (ranges None) or refresh (the pages the edit's pool spans touch) the resolved pool.
-        Asynchronous on the tracer's stream."""
+    def resolve_hash_dag(self, dag: "HashDAG", resolved_pool=None, ranges: "np.ndarray | None" = None, prefix_pool=None, prefix: bool = True) -> "ResolvedHashDAG":
+        """hdt_hash_dag_resolve: fill (ranges None) or refresh (the pages the edit's pool spans touch) the resolved pool and,
+        unless prefix=False, the prefix pool.  Asynchronous on the tracer's stream."""
         torch = _torch()
         if resolved_pool is None:
             resolved_pool = torch.empty(dag.pool.numel(), dtype=torch.int32, device=dag.pool.device)
+        if prefix_pool is None and prefix:
+            prefix_pool = torch.empty(dag.pool.numel(), dtype=torch.int32, device=dag.pool.device)
         pod = dag.pod()
         rptr, n = (None, 0)
         if ranges is not None:
             ranges = np.ascontiguousarray(ranges)
             assert ranges.dtype.itemsize == 24
             rptr, n = ranges.ctypes.data, len(ranges)
-        _check(self._lib.hdt_hash_dag_resolve(self._ctx, pod, len(pod), resolved_pool.data_ptr(), resolved_pool.numel(), rptr, n))
-        return ResolvedHashDAG(dag, resolved_pool)
+        _check(self._lib.hdt_hash_dag_resolve(self._ctx, pod, len(pod), resolved_pool.data_ptr(), _ptr(prefix_pool), resolved_pool.numel(), rptr, n))
+        return ResolvedHashDAG(dag, resolved_pool, prefix_pool)
 
     def rebuild_color_leaf(self, ops: np.ndarray, old_leaf: "CompressedColorLeaf | None" = None, device=None):
         """Re-encode a colour leaf on the GPU from an op list (color_leaf.OP_DTYPE records = hdt_color_op), see
@@ -512,3 +517,7 @@ class DAGTracer:
 
     def launch_count(self) -> int:
         return int(self._lib.hdt_launch_count(self._ctx))
+
+    def recorded_color_passes(self) -> int:
+        """Colour passes that read the paths pass' ancestor records instead of walking the DAG (OPT_COLORS_RECORDED)."""
+        return int(self._lib.hdt_recorded_color_passes(self._ctx))

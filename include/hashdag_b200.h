@@ -54,9 +54,12 @@ typedef struct hdt_hash_dag {                                                   
     uint32_t _pad;
 } hdt_hash_dag;
 
-typedef struct hdt_resolved_hash_dag {      /* library format, 40 B: the HashDAG as the reference passes it + a copy of its pool in which every */
+typedef struct hdt_resolved_hash_dag {      /* library format, 48 B: the HashDAG as the reference passes it + a copy of its pool in which every */
     hdt_hash_dag dag;                        /* child pointer already holds the child's physical word index (hdt_hash_dag_resolve)               */
     const uint32_t* resolved_pool;           /* device, pool_top * 512 words, caller-owned */
+    const uint32_t* prefix_pool;             /* device, same size, caller-owned, or NULL: per child-pointer word of the levels below the colour
+                                                tree, the voxels under the node's earlier children (what trace_colors otherwise adds up by
+                                                loading every preceding sibling, tracer.cu:391-420) */
 } hdt_resolved_hash_dag;
 
 typedef struct hdt_color_leaf {                                                                /* CompressedColorLeaf, vwsc.h:157-191: 104 B */
@@ -121,9 +124,16 @@ enum {
                                     Only valid while nothing queued on the tracer's stream modifies the DAG (static scene, or
                                     edits applied after hdt_sync()).  env HDT_BEAM_PREFETCH */
     HDT_OPT_BEAM_SERIAL = 4,     /* diagnostics, default 0.  1: the per-ray kernels wait for the beam kernel instead of racing it */
-    HDT_OPT_EXCHANGE_FUSED = 5   /* default 0.  1 (needs an exchange, hdt_exchange_*): every shadows pass -- the pass that writes a frame's final
+    HDT_OPT_EXCHANGE_FUSED = 5,  /* default 0.  1 (needs an exchange, hdt_exchange_*): every shadows pass -- the pass that writes a frame's final
                                     colours -- also stores them into rank 0's frame and its last CTA signals the arrival, so hdt_exchange_frame has
-                                    nothing left to copy.  While set, every shadows pass must be followed by hdt_exchange_frame. */
+                                    nothing left to copy.  While set, every shadows pass must be followed by hdt_exchange_frame (a second
+                                    shadows pass before it returns HDT_ERR_STATE). */
+    HDT_OPT_COLORS_RECORDED = 6, /* default 1 (env HDT_COLORS_RECORDED).  For a HDT_DAG_HASH_RESOLVED DAG with a prefix pool, trace_paths also
+                                    records, per hit pixel, where the path leaves each ancestor below the colour tree, and trace_colors of the
+                                    SAME DAG (same resolved pool, prefix pool and root) reads the voxel's colour index off those records
+                                    instead of walking the DAG again.  0: always the full walk of tracer.cu:300-430. */
+    HDT_OPT_EXCHANGE_TIMEOUT_MS = 7 /* how long a framebuffer-exchange wait polls before it gives up and drops the frame (default 20000;
+                                    0 = for ever).  A timeout is reported (HDT_ERR_STATE) by the next host-synchronising call. */
 };
 int hdt_set_option(hdt_ctx* ctx, int option, int value);
 /* Diagnostics of the last beam pre-pass: out[0..3] = tiles that start at the root / resume below it /
@@ -197,7 +207,8 @@ int hdt_assemble_colors(hdt_ctx* ctx, const uint32_t* gathered_dev, uint32_t* fr
  * rank 0's credit, scatter their tiles and signal; rank 0 scatters its own tiles and waits for world-1 arrivals, after
  * which work queued on its stream may read the frame.  Rank 0 calls hdt_exchange_release once that work is queued; it
  * publishes the credit that lets the others overwrite the frame.  A peer that never arrives makes the wait give up after
- * ~2 s of GPU time: hdt_sync() then returns HDT_ERR_STATE. */
+ * HDT_OPT_EXCHANGE_TIMEOUT_MS: the frame is dropped (nothing is stored or signalled for it) and the next host-synchronising
+ * call (hdt_sync, hdt_resolve_*, hdt_read_*, hdt_timer_end) returns HDT_ERR_STATE. */
 #define HDT_IPC_HANDLE_BYTES 64
 int hdt_exchange_create(hdt_ctx* ctx, uint8_t ipc_handle_out[HDT_IPC_HANDLE_BYTES], void** frame_dev_out);
 int hdt_exchange_open(hdt_ctx* ctx, const uint8_t ipc_handle[HDT_IPC_HANDLE_BYTES]);
@@ -250,14 +261,21 @@ int hdt_apply_ranges_host(hdt_ctx* ctx, uint32_t* dst_dev, const uint32_t* paylo
 /* Fill (ranges_host == NULL: all pool_top pages) or refresh (the pages the n_ranges pool spans of an edit touch, as
  * given to hdt_apply_ranges[_host]) `resolved_pool_dev`, a caller-owned device buffer of pool_top * 512 words
  * (capacity_words >= that): a copy of the HashDAG's pool with the same physical layout whose child pointers have been
- * pushed through the page table once.  Pass it with the DAG as hdt_resolved_hash_dag / HDT_DAG_HASH_RESOLVED wherever a
- * HashDAG is accepted: a descent then costs two dependent loads instead of three; frames are identical.  Call it after the
- * pool and page table of an edit have been applied; asynchronous (tracer's stream, ordered before later frames). */
-int hdt_hash_dag_resolve(hdt_ctx* ctx, const hdt_hash_dag* dag, size_t dag_size, uint32_t* resolved_pool_dev, uint64_t capacity_words,
-                         const hdt_range* ranges_host, uint32_t n_ranges);
+ * pushed through the page table once -- and, if `prefix_pool_dev` is not NULL (same size), the prefix pool described at
+ * hdt_resolved_hash_dag.  Pass them with the DAG as hdt_resolved_hash_dag / HDT_DAG_HASH_RESOLVED wherever a HashDAG is
+ * accepted: a descent then costs two dependent loads instead of three and trace_colors no longer walks the DAG; frames
+ * are identical.  Call it after the pool and page table of an edit have been applied; asynchronous (tracer's stream,
+ * ordered before later frames).
+ * Nothing is assumed about pool words no node occupies (page tails, unused pages): they may hold anything, the
+ * reference does not clear its pool (hash_table.cpp:60-76); every index read from the pool is bounds-checked. */
+int hdt_hash_dag_resolve(hdt_ctx* ctx, const hdt_hash_dag* dag, size_t dag_size, uint32_t* resolved_pool_dev, uint32_t* prefix_pool_dev_or_null,
+                         uint64_t capacity_words, const hdt_range* ranges_host, uint32_t n_ranges);
 
 /* Kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t hdt_launch_count(const hdt_ctx* ctx);
+/* Colour passes of this context that read the ancestor records of the paths pass (HDT_OPT_COLORS_RECORDED) instead of
+ * walking the DAG (diagnostics: which route did hdt_resolve_colors take?). */
+uint64_t hdt_recorded_color_passes(const hdt_ctx* ctx);
 int hdt_version(void);
 
 #ifdef __cplusplus

@@ -45,7 +45,7 @@ def test_pod_sizes_match_reference_layouts():
     assert ctypes.sizeof(tracer.ToolInfo) == 44
     # library formats next to the path
     from hashdag_b200 import color_leaf, edits
-    assert len(tracer.ResolvedHashDAG(tracer.HashDAG(None, None, 1, 0, 17), None).pod()) == 40     # hdt_resolved_hash_dag
+    assert len(tracer.ResolvedHashDAG(tracer.HashDAG(None, None, 1, 0, 17), None).pod()) == 48     # hdt_resolved_hash_dag
     assert color_leaf.OP_DTYPE.itemsize == 32 and edits.RANGE_DTYPE.itemsize == 24                  # hdt_color_op, hdt_range
 
 

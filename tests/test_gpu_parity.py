@@ -215,7 +215,7 @@ def test_resolved_hash_dag_gives_the_same_frames(tr, levels):
     t = tr(levels)
     dag, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
     res = t.resolve_hash_dag(dag)
-    assert res.kind == tracer.DAG_HASH_RESOLVED and len(res.pod()) == 40
+    assert res.kind == tracer.DAG_HASH_RESOLVED and len(res.pod()) == 48 and res.prefix_pool is not None
     info = _info(s)
     # the resolved pool differs from the pool exactly in the child-pointer words
     t.sync()
@@ -309,6 +309,7 @@ def test_peer_exchange_gives_up_on_a_missing_rank():
     t = tracer.DAGTracer(True, W, H, 13)
     t.set_partition(0, 2, 5)
     t.exchange_create()
+    t.set_option(tracer.OPT_EXCHANGE_TIMEOUT_MS, 300)
     t.exchange_frame()                            # rank 1 never arrives
     with pytest.raises(tracer.TracerError):
         t.sync()
@@ -408,3 +409,106 @@ def test_replay_file_drives_the_tracer_like_the_engine(tr, tmp_path):
     oc, _ = hdo.trace_colors(odag, ocol, op)
     osh, _ = hdo.trace_shadows(odag, prm, op, oc, 1.0, 0.0)
     assert np.array_equal(last, osh)
+
+
+def _reachable_words(scene):
+    """Physical word indices of every word a walk of the HashDAG from its root can touch (headers, child pointers, leaves)."""
+    pool, table = scene.hash_pool, scene.hash_page_table.astype(np.int64)
+    phys = lambda v: table[v >> 9] * 512 + (v & 511)
+    used = []
+    frontier = np.array([scene.hash_first_node_index], dtype=np.int64)
+    for level in range(scene.levels - 2):
+        h = phys(frontier)
+        hdr = pool[h].astype(np.int64)
+        n = np.array([bin(int(x) & 0xFF).count("1") for x in np.unique(hdr & 0xFF)])   # popcount table of the masks present
+        lut = np.zeros(256, np.int64)
+        lut[np.unique(hdr & 0xFF)] = n
+        cnt = lut[hdr & 0xFF]
+        idx = np.repeat(h, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)) + 1
+        used += [h, idx]
+        frontier = np.unique(pool[idx].astype(np.int64))
+    h = phys(frontier)
+    used += [h, h + 1]
+    return np.unique(np.concatenate(used))
+
+
+@pytest.mark.parametrize("levels,fp", [(13, 10), (16, 11), (17, 10)])
+def test_recorded_colors_equal_the_full_walk(tr, levels, fp):
+    """HDT_OPT_COLORS_RECORDED: trace_paths leaves per hit pixel where its path leaves each ancestor below the colour tree,
+    trace_colors reads the colour index off the prefix pool.  Same pixels as the walk of tracer.cu:300-430 (option off) and
+    as the oracle: every decoding view, the tool overlay, beams on and off, hostile cameras."""
+    from hashdag_b200 import tracer
+    s = get_scene(levels, fp)
+    t = tr(levels)
+    dag, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
+    res = t.resolve_hash_dag(dag)
+    odag, ocol = hdo.make_dag(s, hdo.DAG_HASH), hdo.make_colors(s, hdo.COLORS_HASH)
+    info = _info(s)
+    c = 1 << (levels - 1)
+    tool = tracer.ToolInfo(0, (c, int(s.heights[(c, c)]), c), 60.0, (0, 0, 0), (0, 0, 0))
+    views = [(tracer.DEBUG_NONE, False), (tracer.DEBUG_COLOR_BITS, False), (tracer.DEBUG_MIN_COLOR, False), (tracer.DEBUG_MAX_COLOR, False),
+             (tracer.DEBUG_WEIGHT, False), (tracer.DEBUG_NONE, True)]
+    for beams in (1, 0):
+        t.set_option(tracer.OPT_BEAMS, beams)
+        for cam in scene_cameras(s, 2, fp) + _special_cameras(s, fp)[:3]:
+            frames = {}
+            for recorded in (1, 0):
+                t.set_option(tracer.OPT_COLORS_RECORDED, recorded)
+                before = t.recorded_color_passes()
+                t.resolve_paths(cam, info, res)
+                frames[recorded] = []
+                for dbg, overlay in views:
+                    t.resolve_colors(res, col, dbg, 0, tool if overlay else None, overlay)
+                    frames[recorded].append(t.read_colors())
+                t.resolve_colors(res, col, tracer.DEBUG_INDEX, 3)          # a view the records cannot serve: full walk
+                assert t.recorded_color_passes() - before == (len(views) if recorded else 0)
+            for a, b in zip(frames[1], frames[0]):
+                assert np.array_equal(a, b), f"{(a != b).sum()} pixels differ between the recorded route and the walk"
+            oc, _ = hdo.trace_colors(odag, ocol, t.read_paths())
+            assert np.array_equal(frames[1][0], oc)
+    t.set_option(tracer.OPT_BEAMS, 1)
+    t.set_option(tracer.OPT_COLORS_RECORDED, 1)
+    # a colours pass for ANOTHER DAG than the paths frame was traced in must not use the records
+    t.resolve_paths(scene_cameras(s, 1, fp)[0], info, res)
+    before = t.recorded_color_passes()
+    t.resolve_colors(dag, col)
+    other = t.resolve_hash_dag(dag)
+    t.resolve_colors(other, col)
+    assert t.recorded_color_passes() == before
+    t.resolve_colors(res, col)
+    assert t.recorded_color_passes() == before + 1
+
+
+def test_resolve_ignores_what_lies_behind_the_nodes(tr):
+    """The reference never clears its pool (cudaMalloc'd, hash_table.cpp:60-76): words no node occupies may hold anything.
+    With every such word set to 0xFFFFFFFF the resolved and prefix pools must still serve the same frames."""
+    import torch
+    from hashdag_b200 import tracer
+    levels = 13
+    s = get_scene(levels, 10)
+    t = tr(levels)
+    live = _reachable_words(s)
+    dirty = np.full(s.hash_pool.size + 3 * 512, 0xFFFFFFFF, dtype=np.uint32)       # garbage pages behind pool_top too
+    dirty[live] = s.hash_pool[live]
+    assert (dirty[: s.hash_pool.size] != s.hash_pool).sum() > 1000
+    clean, col = tracer.HashDAG.from_scene(s), tracer.HashDAGColors.from_scene(s)
+    bad = tracer.HashDAG(tracer._to_device(dirty, "cuda:0"), clean.page_table, clean.pool_top, clean.first_node_index, levels)
+    res_clean, res_bad = t.resolve_hash_dag(clean), t.resolve_hash_dag(bad)
+    t.sync()
+    info = _info(s)
+    for cam in scene_cameras(s, 2, 10):
+        out = []
+        for d in (res_clean, res_bad, bad):
+            t.resolve_paths(cam, info, d)
+            p = t.read_paths()
+            t.resolve_colors(d, col)
+            t.resolve_shadows(cam, info, d, 1.0, 0.0)
+            out.append((p, t.read_colors()))
+        for p, c in out[1:]:
+            assert np.array_equal(p, out[0][0]) and np.array_equal(c, out[0][1])
+    # live words of the two resolved / prefix pools agree
+    a, b = res_clean.resolved_pool.cpu().numpy().view(np.uint32), res_bad.resolved_pool.cpu().numpy().view(np.uint32)
+    assert np.array_equal(a[live], b[live])
+    a, b = res_clean.prefix_pool.cpu().numpy().view(np.uint32), res_bad.prefix_pool.cpu().numpy().view(np.uint32)
+    assert np.array_equal(a[live], b[live])
+    torch.cuda.synchronize()
