@@ -190,6 +190,27 @@ def product_implementation(args, world):
     }
 
 
+class stdout_to_stderr:
+    """The reference prints its progress with printf (hash_dag_factory.cpp, memory.cpp); bench.py's stdout carries ONE JSON
+    line, so while reference code runs, file descriptor 1 points at stderr (C stdio flushed on both sides)."""
+
+    def __enter__(self):
+        import ctypes
+        self.libc = ctypes.CDLL(None)
+        sys.stdout.flush()
+        self.libc.fflush(None)
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        self.libc.fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def time_reference_kernels(rt, poses, info, step_ids, warmup_ids, dk, ck):
     """The reference's three synchronous calls per frame (dag_tracer.cu:116-219), timed by its own cudaEvents (:130-138)."""
     for i in warmup_ids:
@@ -211,6 +232,8 @@ def run_reference_cuda(args):
     W, H = resolution(args, 1)
     scene, poses = workloads.build_workload(args.levels, args.footprint_log2, args.poses)
     info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    guard = stdout_to_stderr()
+    guard.__enter__()
     rt = ref.RefTracer(args.levels, W, H)
     rt.load_scene(scene)
     hashed = args.dag == "hash"
@@ -230,6 +253,8 @@ def run_reference_cuda(args):
             tp, tc, ts = tp + a, tc + b, ts + c
             rays += W * H + hits[i % len(poses)]
     total_ms = tp + tc + ts
+    rt.close()
+    guard.__exit__()
     print(json.dumps({
         "impl": "reference-cuda", "metric": METRIC, "value": rays / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "dtype": "f32+f64+u32", "data": "synthetic",
@@ -665,15 +690,16 @@ def run_ours(args):
             for i in sample_ids[:2]:
                 tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, host_frame)
                 ours_img[i] = host_frame.numpy().view(np.uint32).reshape(H, W).copy()
-            rt = ref.RefTracer(args.levels, W, H)
-            rt.load_scene(scene)
-            dk, ck = (1, 3) if hashed else (0, 1)
-            ref_ms = time_reference_kernels(rt, poses, info, step_ids, warm_ids, dk, ck)
-            ref_bad = 0
-            for i in sample_ids[:2]:
-                rt.resolve_paths(dk, poses[i], info); rt.resolve_colors(dk, ck); rt.resolve_shadows(dk, poses[i], info, 1.0, 0.0)
-                ref_bad += int((rt.read_colors() != ours_img[i]).sum())
-            rt.close()
+            with stdout_to_stderr():
+                rt = ref.RefTracer(args.levels, W, H)
+                rt.load_scene(scene)
+                dk, ck = (1, 3) if hashed else (0, 1)
+                ref_ms = time_reference_kernels(rt, poses, info, step_ids, warm_ids, dk, ck)
+                ref_bad = 0
+                for i in sample_ids[:2]:
+                    rt.resolve_paths(dk, poses[i], info); rt.resolve_colors(dk, ck); rt.resolve_shadows(dk, poses[i], info, 1.0, 0.0)
+                    ref_bad += int((rt.read_colors() != ours_img[i]).sum())
+                rt.close()
             ref_total = sum(ref_ms.values())
             out["ref_cuda"] = {"what": "oracle/_ref: the UNMODIFIED reference kernels (tracer.cu:145-697 via dag_tracer.cu:116-219) compiled for sm_100a, same GPU, "
                                        "DAG and the same K poses, after the timed region; kernel times from the reference's own cudaEvents, three synchronous calls per frame",

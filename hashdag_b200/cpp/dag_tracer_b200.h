@@ -59,7 +59,21 @@ struct CameraView {
     Vector3 forward() const { return { rotation[2][0], rotation[2][1], rotation[2][2] }; }
 };
 struct DAGInfo { Vector3 boundsAABBMin, boundsAABBMax; };
-struct uint3_t { uint32_t x, y, z; };
+// What get_path returns: converts to CUDA's uint3 (or anything with x, y, z) so that `config.path = tracer->get_path(..)`
+// (engine.cpp:597) compiles unchanged, without this header needing the CUDA headers.
+struct uint3_t {
+    uint32_t x, y, z;
+    template <class T, class = decltype(T{}.x, T{}.y, T{}.z)>
+    operator T() const { T t{}; t.x = x; t.y = y; t.z = z; return t; }
+};
+
+// The reference decides at compile time whether trace_colors draws the tool overlay (TOOL_OVERLAY, typedefs.h:70-72;
+// off under BENCHMARK); a host that defines the macro gets the same behaviour from the shim by default.
+#if defined(TOOL_OVERLAY)
+#define HDT_SHIM_TOOL_OVERLAY (TOOL_OVERLAY != 0)
+#else
+#define HDT_SHIM_TOOL_OVERLAY false
+#endif
 
 struct TraceParams { double cam[3], rayMin[3], rayDDx[3], rayDDy[3]; };
 
@@ -100,7 +114,7 @@ public:
     explicit DAGTracer(bool headLess, uint32_t imageWidth = 1920, uint32_t imageHeight = 1080, uint32_t levels = 17, int device = 0)
         : headLess(headLess), width_(imageWidth), height_(imageHeight), levels_(levels)
     {
-        check(hdt_create(imageWidth, imageHeight, levels, device, &ctx_), "hdt_create");
+        require_ok(hdt_create(imageWidth, imageHeight, levels, device, &ctx_), "hdt_create");
     }
     ~DAGTracer() { hdt_destroy(ctx_); }
     DAGTracer(const DAGTracer&) = delete;
@@ -114,17 +128,17 @@ public:
     {
         const TraceParams p = get_trace_params(camera, levels_, dagInfo, width_, height_);
         float ms = 0;
-        check(hdt_resolve_paths(ctx_, dag_kind<TDAG>::value, &dag, sizeof(TDAG), p.cam, p.rayMin, p.rayDDx, p.rayDDy, &ms), "resolve_paths");
+        require_ok(hdt_resolve_paths(ctx_, dag_kind<TDAG>::value, &dag, sizeof(TDAG), p.cam, p.rayMin, p.rayDDx, p.rayDDy, &ms), "resolve_paths");
         return ms;
     }
 
     template <typename TDAG, typename TDAGColors, typename TDebugColors, typename TToolInfo>
     float resolve_colors(const TDAG& dag, const TDAGColors& colors, TDebugColors debugColors, uint32_t debugColorsIndexLevel, TToolInfo toolInfo,
-                         bool toolOverlay = false)
+                         bool toolOverlay = HDT_SHIM_TOOL_OVERLAY)
     {
         static_assert(sizeof(TToolInfo) == sizeof(hdt_tool_info), "ToolInfo layout (tracer.h:33-39)");
         float ms = 0;
-        check(hdt_resolve_colors(ctx_, dag_kind<TDAG>::value, &dag, sizeof(TDAG), colors_kind<TDAGColors>::value, &colors, sizeof(TDAGColors),
+        require_ok(hdt_resolve_colors(ctx_, dag_kind<TDAG>::value, &dag, sizeof(TDAG), colors_kind<TDAGColors>::value, &colors, sizeof(TDAGColors),
                                  int(debugColors), debugColorsIndexLevel, reinterpret_cast<const hdt_tool_info*>(&toolInfo), toolOverlay ? 1 : 0, &ms),
               "resolve_colors");
         return ms;
@@ -135,7 +149,7 @@ public:
     {
         const TraceParams p = get_trace_params(camera, levels_, dagInfo, width_, height_);
         float ms = 0;
-        check(hdt_resolve_shadows(ctx_, dag_kind<TDAG>::value, &dag, sizeof(TDAG), p.cam, p.rayMin, p.rayDDx, p.rayDDy, shadowBias, fogDensity, &ms),
+        require_ok(hdt_resolve_shadows(ctx_, dag_kind<TDAG>::value, &dag, sizeof(TDAG), p.cam, p.rayMin, p.rayDDx, p.rayDDy, shadowBias, fogDensity, &ms),
               "resolve_shadows");
         return ms;
     }
@@ -144,17 +158,18 @@ public:
     {
         uint32_t v[3] = { 0, 0, 0 };
         if (headLess) return { 0, 0, 0 };   // dag_tracer.cu:244
-        check(hdt_get_path(ctx_, posX, posY, v), "get_path");
+        require_ok(hdt_get_path(ctx_, posX, posY, v), "get_path");
         return { v[0], v[1], v[2] };
     }
 
     // Additions the reference lacks: full-frame read-back (its harness reads the cudaArrays).
-    void read_paths(uint32_t* host) { check(hdt_read_paths(ctx_, host), "read_paths"); }
-    void read_colors(uint32_t* host) { check(hdt_read_colors(ctx_, host), "read_colors"); }
+    void read_paths(uint32_t* host) { require_ok(hdt_read_paths(ctx_, host), "read_paths"); }
+    void read_colors(uint32_t* host) { require_ok(hdt_read_colors(ctx_, host), "read_colors"); }
     hdt_ctx* context() { return ctx_; }
 
 private:
-    static void check(int rc, const char* what)
+    // (not called `check`: the reference defines a macro of that name, typedefs.h)
+    static void require_ok(int rc, const char* what)
     {
         if (rc != HDT_OK) {   // the reference prints and aborts on any CUDA error
             std::fprintf(stderr, "ERROR hashdag_b200 %s: %d: %s\n", what, rc, hdt_last_error());

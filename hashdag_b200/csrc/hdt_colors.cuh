@@ -129,7 +129,7 @@ __device__ __forceinline__ CompressedColorDev leaf_get_color(const ColorLeafDev&
 // the ~1000 blocks per macro block of a noisy leaf.  Here every round probes K-1 evenly spaced headers at once
 // (independent loads, one latency) and keeps the K-th of the range that contains the answer: log_K(n) rounds.
 #ifndef HDT_COLOR_SEARCH_K
-#define HDT_COLOR_SEARCH_K 8
+#define HDT_COLOR_SEARCH_K 4   // A/B on B200 (profiles/r2_ab.md): 4 -> 0.075 ms, 8 -> 0.079, 16 -> 0.092 per 1080p colour pass
 #endif
 __device__ __forceinline__ CompressedColorDev leaf_get_color_wide(const ColorLeafDev& l, u64 colorIndex)
 {
@@ -374,7 +374,7 @@ __device__ __forceinline__ u32 color_pixel_recorded(const u32* __restrict__ pref
     const u32 w[kMaxAncestorWords] = { a.x, a.y, a.z, a.w, b.x, b.y };
     u32 below[kMaxAncestorWords];
 #pragma unroll
-    for (u32 i = 0; i < kMaxAncestorWords; ++i) below[i] = (kColorTreeDepth + i + 3 <= levels) ? __ldg(prefix + w[i]) : 0u;
+    for (u32 i = 0; i < kMaxAncestorWords; ++i) below[i] = (kColorTreeDepth + i + 3 <= levels) ? (__ldg(prefix + w[i]) & 0xFFFFFFu) : 0u;   // top byte: leaf mask
     // the colour tree
     u32 colorNodeIndex = 0;
 #pragma unroll 1

@@ -16,8 +16,10 @@ using u16 = uint16_t;
 using u32 = uint32_t;
 using u64 = uint64_t;
 
-#ifndef HDT_LEAF_LATE
-#define HDT_LEAF_LATE 0
+// Any-hit walks (trace_shadows) may visit children in any order -- the result is "is there a voxel", not which one.
+// 0: highest child first like the reference (tracer.cu:493); 1: lowest child first (= front to back for the sun's direction).
+#ifndef HDT_ANYHIT_LOW_FIRST
+#define HDT_ANYHIT_LOW_FIRST 0
 #endif
 constexpr u32 kMaxLevels = 24;   // float node centres stay exact below 2^24
 constexpr u32 kPageWords = 512;  // C_pageSize, hash_dag_globals.h:10
@@ -44,6 +46,8 @@ struct PixelMap {
 //             table (hash_table.h:156-173).  Nodes never straddle a page (hash_table.h:416-442),
 //             so header and child pointers of one node share one translation.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 first_child_mask(uint2 leaf);
+
 struct BasicDagDev {
     const u32* __restrict__ data;
     __device__ __forceinline__ u32 root() const { return 0; }
@@ -54,6 +58,7 @@ struct BasicDagDev {
     __device__ __forceinline__ u32 to_handle(u32 ptr) const { return ptr; }
     __device__ __forceinline__ u32 child(u32 h, u32 off) const { return __ldg(data + u32(h + off)); }
     __device__ __forceinline__ uint2 leaf(u32 h) const { return make_uint2(__ldg(data + h), __ldg(data + h + 1)); }
+    __device__ __forceinline__ u32 leaf_first_mask(u32, uint2 l) const { return first_child_mask(l); }
 };
 
 struct HashDagDev {
@@ -68,6 +73,7 @@ struct HashDagDev {
     __device__ __forceinline__ u32 child(u32 h, u32 off) const { return to_handle(__ldg(pool + u32(h + off))); }
     // leaves sit at even bucket positions in 512-word pages: 8-byte aligned (hash_table.h:367-392)
     __device__ __forceinline__ uint2 leaf(u32 h) const { return __ldg(reinterpret_cast<const uint2*>(pool + h)); }
+    __device__ __forceinline__ u32 leaf_first_mask(u32, uint2 l) const { return first_child_mask(l); }
 };
 
 // A HashDAG whose child words have been pushed through the page table ONCE (hdt_hash_dag_resolve, hdt_resolve.cuh):
@@ -75,11 +81,15 @@ struct HashDagDev {
 // holds the physical word index of the child.  A descent is then two dependent loads (child word, child header) like
 // BasicDAG's instead of three.  The caller's pool and page table stay at hand for the two debug views that display the
 // reference's virtual indices.
-struct HashDagResolvedDev {
+// PREFIX: the DAG comes with a prefix pool (hdt_resolve.cuh), whose word at a pointer to a 64-bit leaf also carries the leaf's
+// first-level child mask in its top byte: the traversal reads it (one load, issued beside the pointer load) instead of
+// reducing the 64 bits itself (11 instructions that every lane of a warp pays for whenever one lane is at that level).
+template <bool PREFIX>
+struct HashDagResolvedDevT {
     const u32* __restrict__ pool;        // resolved copy
     const u32* __restrict__ vpool;       // the caller's pool (virtual child pointers)
     const u32* __restrict__ pageTable;
-    const u32* __restrict__ prefix;      // optional: per child-pointer word, the voxels under the node's earlier children (hdt_resolve.cuh)
+    const u32* __restrict__ prefix;      // per child-pointer word: voxels under the node's earlier children | leaf mask << 24; null unless PREFIX
     u32 firstNodeIndex;
     __device__ __forceinline__ u32 to_handle(u32 vptr) const { return __ldg(pageTable + (vptr >> 9)) * kPageWords + (vptr & (kPageWords - 1)); }
     __device__ __forceinline__ u32 root() const { return to_handle(firstNodeIndex); }
@@ -88,9 +98,11 @@ struct HashDagResolvedDev {
     __device__ __forceinline__ u32 raw_child(u32 h, u32 off) const { return __ldg(vpool + u32(h + off)); }
     __device__ __forceinline__ u32 child(u32 h, u32 off) const { return __ldg(pool + u32(h + off)); }
     __device__ __forceinline__ uint2 leaf(u32 h) const { return __ldg(reinterpret_cast<const uint2*>(pool + h)); }
+    __device__ __forceinline__ u32 leaf_first_mask(u32 pointerWord, uint2 l) const { return PREFIX ? (__ldg(prefix + pointerWord) >> 24) : first_child_mask(l); }
 };
+using HashDagResolvedDev = HashDagResolvedDevT<false>;
+using HashDagPrefixDev = HashDagResolvedDevT<true>;
 
-// base_dag.h:16-58
 // Bit k of the result = byte k of the 64-bit leaf is non-zero.  Per word: the carry of (byte & 0x7F) + 0x7F ORed with the
 // byte's own top bit marks a non-zero byte at bit 7 of the byte; the multiplication gathers bits 7/15/23/31 into bits
 // 28..31 (no two partial products meet above bit 23).
@@ -125,35 +137,53 @@ __device__ __forceinline__ bool ray_is_tame(const Ray& r)
     return fabsf(r.ix) <= lim && fabsf(r.iy) <= lim && fabsf(r.iz) <= lim && fabsf(r.ox) <= 3.0e38f && fabsf(r.oy) <= 3.0e38f && fabsf(r.oz) <= 3.0e38f;
 }
 
-// One of the three axis-plane tests of tracer.cu:91-133: if the ray meets the node's mid-plane at
-// t within [tmin, tmax], OR in the octants on the side(s) of the crossing point q = (q1, q2), each
-// side decided with an epsilon band (lo = centre - eps, hi = centre + eps).  Written in PTX so that
-// it becomes exactly 6 FSETP (the range predicate rides on the .AND input of the first pair, so an
-// out-of-range plane yields A = 0), 4 SEL, 2 adds and one LOP3 -- no branches, no extra selects.
-template <u32 HI1, u32 LO1, u32 HI2, u32 LO2>
-__device__ __forceinline__ u32 plane_mask(float tmin, float tmax, float t, float q1, float lo1, float hi1, float q2, float lo2, float hi2)
+// One of the three axis-plane tests of tracer.cu:91-133: if the ray meets the node's mid-plane at t within [tmin, tmax],
+// OR into `mask` the octants on the side(s) of the crossing point q = (q1, q2), each side decided with an epsilon band
+// (lo = centre - eps, hi = centre + eps).  The reference forms, per coordinate, A = (q >= lo ? HI : 0) + (q <= hi ? LO : 0)
+// with LO = ~HI, and ORs A1 & A2.  Here the COMPLEMENT of each A is built in two instructions -- n = (q <= hi ? 0 : LO),
+// then |= HI unless q >= lo -- and one LOP3 does mask | ~(n1 | n2).  The range test rides on the .AND input of the first
+// pair of compares: out of range (or NaN) makes n1 = 0xFF, so the plane contributes nothing.  6 FSETP + 2 SEL + 2 predicated
+// OR + 1 LOP3, no branches.  Bits above bit 7 of the result are junk (the caller masks).
+template <u32 HI1, u32 HI2>
+__device__ __forceinline__ u32 plane_or(u32 mask, float tmin, float tmax, float t, float q1, float lo1, float hi1, float q2, float lo2, float hi2)
 {
     u32 out;
     asm("{\n\t"
         ".reg .pred pin, pa, pb, pc, pd;\n\t"
-        ".reg .u32 a, b, c, d;\n\t"
+        ".reg .u32 n1, n2;\n\t"
         "setp.le.f32 pin, %1, %3;\n\t"
         "setp.le.and.f32 pin, %3, %2, pin;\n\t"
         "setp.ge.and.f32 pa, %4, %5, pin;\n\t"
         "setp.le.and.f32 pb, %4, %6, pin;\n\t"
         "setp.ge.f32 pc, %7, %8;\n\t"
         "setp.le.f32 pd, %7, %9;\n\t"
-        "selp.u32 a, %10, 0, pa;\n\t"
-        "selp.u32 b, %11, 0, pb;\n\t"
-        "selp.u32 c, %12, 0, pc;\n\t"
-        "selp.u32 d, %13, 0, pd;\n\t"
-        "add.u32 a, a, b;\n\t"
-        "add.u32 c, c, d;\n\t"
-        "and.b32 %0, a, c;\n\t"
+        "selp.u32 n1, 0, %11, pb;\n\t"
+        "@!pa or.b32 n1, n1, %10;\n\t"
+        "selp.u32 n2, 0, %13, pd;\n\t"
+        "@!pc or.b32 n2, n2, %12;\n\t"
+        "lop3.b32 %0, %14, n1, n2, 0xF1;\n\t"
         "}"
         : "=r"(out)
-        : "f"(tmin), "f"(tmax), "f"(t), "f"(q1), "f"(lo1), "f"(hi1), "f"(q2), "f"(lo2), "f"(hi2), "n"(HI1), "n"(LO1), "n"(HI2), "n"(LO2));
+        : "f"(tmin), "f"(tmax), "f"(t), "f"(q1), "f"(lo1), "f"(hi1), "f"(q2), "f"(lo2), "f"(hi2), "n"(HI1), "n"(HI1 ^ 0xFFu), "n"(HI2), "n"(HI2 ^ 0xFFu), "r"(mask));
     return out;
+}
+
+// 1 << (4a + 2b + c) for three comparisons a = (ha >= ra), ...: the octant of the ray's mid-point (tracer.cu:57-63).
+__device__ __forceinline__ u32 octant_bit(float hx, float rx, float hy, float ry, float hz, float rz)
+{
+    u32 m;
+    asm("{\n\t"
+        ".reg .pred p4, p2, p1;\n\t"
+        "setp.ge.f32 p4, %1, %2;\n\t"
+        "setp.ge.f32 p2, %3, %4;\n\t"
+        "setp.ge.f32 p1, %5, %6;\n\t"
+        "selp.u32 %0, 16, 1, p4;\n\t"
+        "@p2 shl.b32 %0, %0, 2;\n\t"
+        "@p1 shl.b32 %0, %0, 1;\n\t"
+        "}"
+        : "=r"(m)
+        : "f"(hx), "f"(rx), "f"(hy), "f"(ry), "f"(hz), "f"(rz));
+    return m;
 }
 
 // tracer.cu:19-136 for the node with centre (cx,cy,cz) and half-size `radius`.
@@ -184,16 +214,16 @@ __device__ __forceinline__ u32 intersection_mask(float cx, float cy, float cz, f
     if (isRoot && (tmin >= tmax)) return 0;
 
     const float h = __fmul_rn(0.5f, __fadd_rn(tmin, tmax));
-    u32 mask = 1u << (((__fmul_rn(h, r.dx) >= rx) ? 4u : 0u) + ((__fmul_rn(h, r.dy) >= ry) ? 2u : 0u) + ((__fmul_rn(h, r.dz) >= rz) ? 1u : 0u));
+    u32 mask = octant_bit(__fmul_rn(h, r.dx), rx, __fmul_rn(h, r.dy), ry, __fmul_rn(h, r.dz), rz);
 
     // Plane tests without branches (see plane_mask): an out-of-range plane contributes nothing.
     const float eps = 1e-4f;
     const float rxm = __fsub_rn(rx, eps), rxp = __fadd_rn(rx, eps);
     const float rym = __fsub_rn(ry, eps), ryp = __fadd_rn(ry, eps);
     const float rzm = __fsub_rn(rz, eps), rzp = __fadd_rn(rz, eps);
-    mask |= plane_mask<0xCC, 0x33, 0xAA, 0x55>(tmin, tmax, tx, __fmul_rn(tx, r.dy), rym, ryp, __fmul_rn(tx, r.dz), rzm, rzp);
-    mask |= plane_mask<0xF0, 0x0F, 0xAA, 0x55>(tmin, tmax, ty, __fmul_rn(ty, r.dx), rxm, rxp, __fmul_rn(ty, r.dz), rzm, rzp);
-    mask |= plane_mask<0xF0, 0x0F, 0xCC, 0x33>(tmin, tmax, tz, __fmul_rn(tz, r.dx), rxm, rxp, __fmul_rn(tz, r.dy), rym, ryp);
+    mask = plane_or<0xCC, 0xAA>(mask, tmin, tmax, tx, __fmul_rn(tx, r.dy), rym, ryp, __fmul_rn(tx, r.dz), rzm, rzp);
+    mask = plane_or<0xF0, 0xAA>(mask, tmin, tmax, ty, __fmul_rn(ty, r.dx), rxm, rxp, __fmul_rn(ty, r.dz), rzm, rzp);
+    mask = plane_or<0xF0, 0xCC>(mask, tmin, tmax, tz, __fmul_rn(tz, r.dx), rxm, rxp, __fmul_rn(tz, r.dy), rym, ryp);
     return mask;
 }
 
@@ -308,18 +338,18 @@ struct Walker {
             pending ^= 1u << nl;
             const uint2 e = stack[nl];
             handle = e.x; cm = e.y & 0xFF; vm = e.y >> 8;
-            // centre of the ancestor `level - nl` levels up: it is the cell of size S = 2*ra that
-            // contains the current centre.  (c - ra) lies strictly inside (corner - S/2, corner + S/2),
-            // so rounding it to a multiple of S (add/subtract 1.5*2^23*S) yields the corner exactly.
+            // centre of the ancestor `level - nl` levels up: the cell of size S = 2*ra that contains the current centre.  Adding
+            // 1.5*2^23*S (one ulp = S) with rounding towards -inf drops the centre's offset inside that cell exactly
+            // (coordinates are far below 2^22*S), subtracting it again leaves the cell's corner, + ra its centre.
             const float ra = __uint_as_float(__float_as_uint(radius) + ((level - nl) << 23));
             const float magic = __fmul_rn(ra, 25165824.0f);   // 1.5 * 2^24 * ra = 1.5 * 2^23 * S
-            cx = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(cx, ra), magic), magic), ra);
-            cy = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(cy, ra), magic), magic), ra);
-            cz = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(cz, ra), magic), magic), ra);
+            cx = __fadd_rn(__fsub_rn(__fadd_rd(cx, magic), magic), ra);
+            cy = __fadd_rn(__fsub_rn(__fadd_rd(cy, magic), magic), ra);
+            cz = __fadd_rn(__fsub_rn(__fadd_rd(cz, magic), magic), ra);
             radius = ra;
             level = nl;
         }
-        const u32 child = ORDERED ? table_child(block, vm) : top_bit(vm);
+        const u32 child = ORDERED ? table_child(block, vm) : HDT_ANYHIT_LOW_FIRST ? u32(__ffs(vm) - 1) : top_bit(vm);
         const float4 st = table_step(block, child);
         vm &= ~__float_as_uint(st.w);
         if (ORDERED || vm) stack[level] = make_uint2(handle, (cm & 0xFF) | (vm << 8));
@@ -334,48 +364,21 @@ struct Walker {
         // the arithmetic.  (With `cm = header & 0xFF` the AND sat right behind the LDG in the SASS and the warp stalled
         // there, in front of the arithmetic.)  Users of cm: popc(cm & (bit - 1)) with bit <= 0x80, and the stack push,
         // which masks it.
-#if HDT_LEAF_LATE
-        // Experimental (default off): the same treatment for the 64-bit leaf.  The leaf's first reader becomes
-        // `leaf & expand(mask)`, which needs the finished mask; the reduction to an 8-bit child mask follows.  cm of a
-        // leaf-level node is never read again (its children are bits of `leaf`, no pointer arithmetic), so it is set to vm.
-        bool fresh = false;
         if (level <= leafLevel) {
-            const u32 next = dag.child(handle, __popc(cm & (__float_as_uint(st.w) - 1u)) + 1);
+            const u32 off = __popc(cm & (__float_as_uint(st.w) - 1u)) + 1;
+            const u32 next = dag.child(handle, off);
             if (level < leafLevel) {
                 handle = next;
                 cm = dag.header(next);
             } else {
                 leaf = dag.leaf(next);
-                fresh = true;
-            }
-        } else {
-            cm = second_child_mask(leaf, child);
-        }
-        const u32 hitMask = intersection_mask<false, TAME>(cx, cy, cz, radius, ray);
-        if (fresh) {
-            const u32 lo = (((hitMask & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu, hi = ((((hitMask >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-            vm = first_child_mask(make_uint2(leaf.x & lo, leaf.y & hi));
-            cm = vm;
-        } else {
-            vm = cm & hitMask & 0xFF;
-        }
-        return 0;
-#else
-        if (level <= leafLevel) {
-            const u32 next = dag.child(handle, __popc(cm & (__float_as_uint(st.w) - 1u)) + 1);
-            if (level < leafLevel) {
-                handle = next;
-                cm = dag.header(next);
-            } else {
-                leaf = dag.leaf(next);
-                cm = first_child_mask(leaf);
+                cm = dag.leaf_first_mask(handle + off, leaf);
             }
         } else {
             cm = second_child_mask(leaf, child);
         }
         vm = cm & intersection_mask<false, TAME>(cx, cy, cz, radius, ray) & 0xFF;
         return 0;
-#endif
     }
     // voxel coordinates once step() returned 1: centre = corner + 0.5
     __device__ __forceinline__ void voxel(u32& x, u32& y, u32& z) const { x = __float2uint_rz(cx); y = __float2uint_rz(cy); z = __float2uint_rz(cz); }

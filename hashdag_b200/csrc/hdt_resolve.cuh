@@ -3,10 +3,12 @@
 //   resolved pool  every child pointer pushed through the page table once (HashDagResolvedDev, hdt_device.cuh): a descent
 //                  is two dependent loads (child word, child header) instead of three;
 //   prefix pool    (optional) for every child-pointer word of a node of depth >= 10 -- the levels below the colour tree,
-//                  hash_dag_globals.h:7 -- the number of voxels under the node's EARLIER children, i.e. the sum
-//                  trace_colors forms by loading every preceding sibling (tracer.cu:391-420, get_leaves_count =
-//                  header >> 8, hash_dag_colors.h:28-32; popcount of the 64-bit leaves at the last interior level).
-//                  With it the colour walk needs one load per level instead of 2 + 2 x (earlier siblings).
+//                  hash_dag_globals.h:7 -- the number of voxels under the node's EARLIER children (low 24 bits; a subtree
+//                  of those levels holds < 2^24 voxels, hash_table.h:772), i.e. the sum trace_colors forms by loading every
+//                  preceding sibling (tracer.cu:391-420, get_leaves_count = header >> 8, hash_dag_colors.h:28-32; popcount
+//                  of the 64-bit leaves at the last interior level).  With it the colour walk needs one load per level
+//                  instead of 2 + 2 x (earlier siblings).  Pointer words to 64-bit leaves also carry, in the top byte,
+//                  the leaf's first-level child mask (base_dag.h:16-40) for the traversal (HashDagPrefixDev).
 //
 // The reference's pool is an array of 512-word physical pages; a virtual page belongs to one bucket of one level
 // (hash_table.h:45-63), interior nodes `[header][child pointer] x popc(header & 0xFF)` are packed from the start of a page
@@ -102,13 +104,17 @@ __global__ void __launch_bounds__(128) resolve_pages_kernel(const u32* __restric
     for (u32 k = lane; k < kPageWords; k += 32) {
         u32 sum = 0;
         const u32 own = owner[warp][k];
+        if (leafChildren && own < 0xFFFEu) {   // the leaf this word points at: its first-level child mask
+            const u32 c = words[warp][k];
+            if (u64(c) + 1 < poolWords) sum = first_child_mask(__ldg(reinterpret_cast<const uint2*>(vpool + (c & ~1u)))) << 24;
+        }
         if (counted && own < 0xFFFEu) {
             for (u32 j = own + 1; j < k; ++j) {
                 if (owner[warp][j] != own) continue;            // an earlier pointer of this node that translated to nowhere
                 const u32 c = words[warp][j];
                 if (u64(c) + 1 >= poolWords) continue;
                 if (leafChildren) { const uint2 l = __ldg(reinterpret_cast<const uint2*>(vpool + (c & ~1u))); sum += __popc(l.x) + __popc(l.y); }
-                else sum += __ldg(vpool + c) >> 8;
+                else sum += __ldg(vpool + c) >> 8;          // stays below 2^24: the sum is at most the node's own count24
             }
         }
         prefix[u64(page) * kPageWords + k] = sum;

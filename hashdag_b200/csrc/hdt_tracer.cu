@@ -46,6 +46,9 @@ namespace {
 #ifndef HDT_MIN_BLOCKS
 #define HDT_MIN_BLOCKS 12
 #endif
+#ifndef HDT_MIN_BLOCKS_SHADOWS
+#define HDT_MIN_BLOCKS_SHADOWS HDT_MIN_BLOCKS
+#endif
 #ifndef HDT_MIN_BLOCKS_COLORS
 #define HDT_MIN_BLOCKS_COLORS 16
 #endif
@@ -367,7 +370,7 @@ __device__ __forceinline__ void shadow_pixel(const CameraParams& cam, const Shad
 }
 
 template <class DAG>
-__global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
+__global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS_SHADOWS) trace_shadows_kernel(const CameraParams cam, const ShadowParams sp, const DAG dag, const u32 levels,
                                                                       const PixelMap map, const uint4* __restrict__ paths, const RayPlanes origins,
                                                                       u32* __restrict__ colors, const TraverseTables* __restrict__ tables,
                                                                       const BeamState* __restrict__ beams, const u32 tag, const ExchangeOut xo)
@@ -574,7 +577,16 @@ int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
     return HDT_OK;
 }
 
-struct DagArg { int kind; BasicDagDev basic; HashDagDev hash; HashDagResolvedDev resolved; };
+struct DagArg {
+    int kind; BasicDagDev basic; HashDagDev hash; HashDagResolvedDev resolved;
+    // a resolved HashDAG with a prefix pool, seen through the accessor that reads leaf masks from it (per-ray traversal kernels)
+#ifdef HDT_NO_PREFIX_LEAF_MASK   // A/B switch: traverse through the plain resolved accessor even when a prefix pool is there
+    bool has_prefix() const { return false; }
+#else
+    bool has_prefix() const { return kind == HDT_DAG_HASH_RESOLVED && resolved.prefix != nullptr; }
+#endif
+    HashDagPrefixDev prefixed() const { return HashDagPrefixDev{ resolved.pool, resolved.vpool, resolved.pageTable, resolved.prefix, resolved.firstNodeIndex }; }
+};
 
 int parse_dag(int kind, const void* pod, size_t size, DagArg& out)
 {
@@ -730,7 +742,8 @@ int launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
     // ancestor records for trace_colors: only a resolved HashDAG with a prefix pool can use them
     AncestorPlanes anc{ nullptr, nullptr };
     if (d.kind == HDT_DAG_HASH_RESOLVED && d.resolved.prefix && c->anc[0] && c->useRecorded) anc = AncestorPlanes{ c->anc[0], c->anc[1] };
-    if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
+    if (d.has_prefix()) trace_paths_kernel<HashDagPrefixDev><<<grid, block, 0, c->stream>>>(cam, d.prefixed(), c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
+    else if (d.kind == HDT_DAG_BASIC) trace_paths_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, d.basic, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
     else if (d.kind == HDT_DAG_HASH) trace_paths_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, d.hash, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
     else trace_paths_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, d.resolved, c->levels, c->map, c->ray_planes(0), c->paths, c->tables, beams, tag, anc);
     HDT_LAUNCHED("trace_paths_kernel");
@@ -813,7 +826,8 @@ int finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const S
         xo = ExchangeOut{ c->xBlock, c->xCtasDone, c->map.rank != 0 ? &k->arrivals : nullptr };
         c->xFusedSeq = seq;
     }
-    if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
+    if (d.has_prefix()) trace_shadows_kernel<HashDagPrefixDev><<<grid, block, 0, c->stream>>>(cam, sp, d.prefixed(), c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
+    else if (d.kind == HDT_DAG_BASIC) trace_shadows_kernel<BasicDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.basic, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
     else if (d.kind == HDT_DAG_HASH) trace_shadows_kernel<HashDagDev><<<grid, block, 0, c->stream>>>(cam, sp, d.hash, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
     else trace_shadows_kernel<HashDagResolvedDev><<<grid, block, 0, c->stream>>>(cam, sp, d.resolved, c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
     HDT_LAUNCHED("trace_shadows_kernel");

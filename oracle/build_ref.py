@@ -22,7 +22,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src"
 OUT_DIR = os.path.join(HERE, "_ref")
 HARNESS = os.path.join(HERE, "ref_harness", "ref_harness.cu")
-HARNESS_FILES = [HARNESS, os.path.join(HERE, "ref_harness", "ref_harness_edits.cpp"), os.path.join(HERE, "ref_harness", "ref_harness_shared.h")]
+# compiled: the harness proper, the reference's CPU edit code, and the drop-in proof (the product's C++ shim driven with the
+# reference's own types, linked against hashdag_b200/libhashdag_b200.so); the headers only count for staleness
+HARNESS_FILES = [HARNESS, os.path.join(HERE, "ref_harness", "ref_harness_edits.cpp"), os.path.join(HERE, "ref_harness", "ref_dropin.cu"),
+                 os.path.join(HERE, "ref_harness", "ref_harness_shared.h"), os.path.join(HERE, "ref_harness", "ref_harness_std.h"),
+                 os.path.join(HERE, "ref_harness", "ref_harness_globals.h"),
+                 os.path.join(os.path.dirname(HERE), "hashdag_b200", "cpp", "dag_tracer_b200.h"), os.path.join(os.path.dirname(HERE), "include", "hashdag_b200.h")]
+PRODUCT_DIR = os.path.join(os.path.dirname(HERE), "hashdag_b200")
 
 # (depth, width, height): golden/parity variants are small, the bench variant is the headline config
 VARIANTS = [
@@ -88,10 +94,11 @@ def build_variant(depth, width, height, force=False, verbose=True, overlay=False
     open(tpath, "w").write(text)
     # .cu files (and the harness) are CUDA; the reference's .cpp files are host C++ that only
     # needs the CUDA headers -- the same split its CMakeLists.txt makes.
-    src = [os.path.join(stage, "src", f) for f in REF_FILES] + HARNESS_FILES[:2]
+    src = [os.path.join(stage, "src", f) for f in REF_FILES] + HARNESS_FILES[:3]
     common = ["nvcc", "-std=c++17", "--expt-relaxed-constexpr", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-w", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique",  # several variants share one process
-              "-I" + os.path.join(stage, "stub"), "-I" + os.path.join(stage, "src"), "-I" + os.path.join(HERE, "ref_harness")]
+              "-I" + os.path.join(stage, "stub"), "-I" + os.path.join(stage, "src"), "-I" + os.path.join(HERE, "ref_harness"),
+              "-I" + os.path.join(PRODUCT_DIR, "cpp")]
     if verbose:
         print(f"[build_ref] d{depth} {width}x{height} -> {os.path.relpath(out, HERE)}", flush=True)
     procs, objs = [], []
@@ -104,7 +111,9 @@ def build_variant(depth, width, height, force=False, verbose=True, overlay=False
         if pr.returncode != 0:
             sys.stderr.write(log[-8000:])
             raise RuntimeError(f"reference build failed for d{depth} {width}x{height}: {f}")
-    r = subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs, capture_output=True, text=True)
+    # the drop-in proof calls the product's C ABI: link the product library, found at run time relative to oracle/_ref/
+    r = subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs +
+                       ["-L" + PRODUCT_DIR, "-lhashdag_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../hashdag_b200"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-4000:] + r.stderr[-8000:])
         raise RuntimeError(f"reference link failed for d{depth} {width}x{height}")

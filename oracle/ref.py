@@ -72,6 +72,12 @@ class RefTracer:
             u3 = C.POINTER(C.c_uint32)
             l.ref_get_values.argtypes = [u3, u3, C.c_void_p]
             l.ref_is_empty.argtypes = [C.c_uint32, u3, u3]
+        if hasattr(l, "ref_dropin_tick"):   # oracle/ref_harness/ref_dropin.cu: the product's C++ shim driven with the reference's own types
+            l.ref_dropin_tick.argtypes = [C.c_int, d, d, d, d, C.c_int, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_uint32, C.c_uint32,
+                                          C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+            l.ref_dropin_read_paths.argtypes = [C.c_void_p]
+            l.ref_dropin_read_colors.argtypes = [C.c_void_p]
+        self._dropin = False
         if l.ref_init(device) != 0:
             raise RuntimeError("ref_init failed (no CUDA device?)")
         self.scene = None
@@ -80,8 +86,31 @@ class RefTracer:
     def close(self):
         """Release the reference's allocations (its leak check aborts the process otherwise)."""
         if self.lib is not None:
+            if self._dropin:
+                self.lib.ref_dropin_shutdown()
             self.lib.ref_shutdown()
             self.lib = None
+
+    # -- the drop-in proof (ref_dropin.cu): Engine::tick's tracer calls made on hashdag_b200::DAGTracer with the reference's structs
+    def dropin_tick(self, current_dag, camera, info, debug_colors=0, debug_level=0, shadows=True, shadow_bias=1.0, fog_density=0.0, pos=(0, 0)):
+        """current_dag: engine.h's EDag (0 uncompressed, 1 compressed, 2 colour errors, 3 HashDAG).  -> ((paths, colours, shadows) ms, config.path)"""
+        if not self._dropin:
+            assert self.lib.ref_dropin_init(0) == 0
+            self._dropin = True
+        times, path = (C.c_double * 3)(), (C.c_uint32 * 3)()
+        assert self.lib.ref_dropin_tick(int(current_dag), _d(camera.position), _d(camera.rotation), _d(info.bounds_min), _d(info.bounds_max), int(debug_colors),
+                                        int(debug_level), int(bool(shadows)), shadow_bias, fog_density, int(pos[0]), int(pos[1]), times, path) == 0
+        return tuple(times), tuple(path)
+
+    def dropin_read_paths(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint32)
+        assert self.lib.ref_dropin_read_paths(out.ctypes.data) == 0
+        return out
+
+    def dropin_read_colors(self):
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        assert self.lib.ref_dropin_read_colors(out.ctypes.data) == 0
+        return out
 
     def load_scene(self, scene, with_hash=True, with_colors=True, with_uncompressed=False, extra_pool_pages=4096):
         assert scene.levels == self.depth

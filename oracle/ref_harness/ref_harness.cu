@@ -8,6 +8,10 @@
 #include "ref_harness_shared.h"
 
 namespace refh {
+BasicDAG g_basic;
+BasicDAGCompressedColors g_compressed;
+BasicDAGUncompressedColors g_uncompressed;
+BasicDAGColorErrors g_errors;
 HashDAG g_hash;
 HashDAGColors g_hashColors;
 bool g_hasHash = false, g_hasHashColors = false;
@@ -16,10 +20,6 @@ using namespace refh;
 
 namespace {
 std::unique_ptr<DAGTracer> g_tracer;
-BasicDAG g_basic;
-BasicDAGCompressedColors g_compressed;
-BasicDAGUncompressedColors g_uncompressed;
-BasicDAGColorErrors g_errors;
 
 CameraView make_camera(const double pos[3], const double rot[9])
 {

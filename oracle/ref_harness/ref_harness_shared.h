@@ -2,40 +2,7 @@
 // the reference's CPU edit code, which only instantiates under a host compiler -- hash_dag_edits.h replaces its
 // `if constexpr` by `if (true)` when __CUDACC__ is defined).  TEST INFRASTRUCTURE, see ref_harness.cu.
 #pragma once
-#include <cstdint>
-#include <cstdio>
-#include <cstring>
-#include <memory>
-#include <string>
-#include <vector>
-#include <mutex>
-#include <atomic>
-#include <unordered_map>
-#include <array>
-#include <random>
-#include <set>
-#include <limits>
-#include <chrono>
-#include <type_traits>
-#include <cmath>
-#include <sstream>
-#include <fstream>
-#include <iostream>
-#include <iomanip>
-#include <thread>
-#include <unordered_set>
-#include <map>
-#include <functional>
-#include <algorithm>
-#include <numeric>
-#include <condition_variable>
-#include <future>
-#include <queue>
-#include <deque>
-#include <list>
-#include <cassert>
-#include <cstdlib>
-#include <filesystem>
+#include "ref_harness_std.h"
 
 // The frame surfaces, the HashTable pointers and the colour arrays are private in the reference
 // and it has no full-frame read-back; the harness alone looks inside.
@@ -51,8 +18,4 @@
 #undef private
 #undef protected
 
-namespace refh {
-extern HashDAG g_hash;
-extern HashDAGColors g_hashColors;
-extern bool g_hasHash, g_hasHashColors;
-}
+#include "ref_harness_globals.h"

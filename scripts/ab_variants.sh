@@ -8,13 +8,13 @@ cd "$(dirname "$0")/.."
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared"
 VARIANTS=(
   "base:"
-  "leaflate:-DHDT_LEAF_LATE=1"
-  "blocks10:-DHDT_MIN_BLOCKS=10"
-  "blocks8:-DHDT_MIN_BLOCKS=8"
-  "search4:-DHDT_COLOR_SEARCH_K=4"
-  "search16:-DHDT_COLOR_SEARCH_K=16"
-  "colreg12:-DHDT_MIN_BLOCKS_COLORS_RECORDED=12"
-  "colreg8:-DHDT_MIN_BLOCKS_COLORS_RECORDED=8"
+  "noleafmask:-DHDT_NO_PREFIX_LEAF_MASK=1"
+  "lowfirst:-DHDT_ANYHIT_LOW_FIRST=1"
+  "shblocks10:-DHDT_MIN_BLOCKS_SHADOWS=10"
+  "cta64:-DHDT_BLOCK_W=8 -DHDT_BLOCK_H=8 -DHDT_MIN_BLOCKS=24 -DHDT_MIN_BLOCKS_COLORS=32 -DHDT_MIN_BLOCKS_COLORS_RECORDED=32"
+  "cta256:-DHDT_BLOCK_W=16 -DHDT_BLOCK_H=16 -DHDT_MIN_BLOCKS=6 -DHDT_MIN_BLOCKS_COLORS=8 -DHDT_MIN_BLOCKS_COLORS_RECORDED=8"
+  "search3:-DHDT_COLOR_SEARCH_K=3"
+  "colhoist:-DHDT_COLORS_HOIST=1"
 )
 mkdir -p ab_libs
 if [ "$1" = "build" ]; then

@@ -22,9 +22,10 @@ from oracle import ref  # noqa: E402
 def main(out_dir):
     os.makedirs(out_dir, exist_ok=True)
     for name in gu.RECIPES:
-        scene = gu.recipe_scene(name)
+        with_unc = name in gu.UNCOMPRESSED_RECIPES     # BasicDAGUncompressedColors / BasicDAGColorErrors views too (basic_dag.h:122-242)
+        scene = gu.recipe_scene(name, uncompressed=with_unc)
         info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
-        rt = ref.shared(scene, gu.W, gu.H, name)
+        rt = ref.shared(scene, gu.W, gu.H, name, with_uncompressed=with_unc)
         has_hash_colors = scene.levels - 2 > 10
         poses = gu.recipe_poses(scene)
         arrays = {}
@@ -52,9 +53,16 @@ def main(out_dir):
             assert (p[..., 3] == 0).all()
             arrays[f"paths_{i}"] = p[..., :3].copy()
             arrays[f"colors_{i}"], arrays[f"shadows_{i}"], arrays[f"fog_{i}"] = c, s, f
+            if with_unc:
+                rt.resolve_paths(0, pose, info)
+                rt.resolve_colors(0, 0)
+                arrays[f"uncompressed_{i}"] = rt.read_colors()
+                rt.resolve_colors(0, 2)
+                arrays[f"errors_{i}"] = rt.read_colors()
+                assert (arrays[f"uncompressed_{i}"] != c).any(), "uncompressed colours never differ from the compressed ones: nothing is pinned"
             print(name, "pose", i, "hits", int(p[..., :3].any(-1).sum()), flush=True)
         meta = dict(recipe=name, n_voxels=int(scene.n_voxels), basic_words=int(scene.basic.size), has_hash_colors=bool(has_hash_colors),
-                    fog=gu.FOG, poses=[gu.pose_to_list(p) for p in poses], generator="tests/golden/make_golden.py",
+                    fog=gu.FOG, uncompressed_views=bool(with_unc), poses=[gu.pose_to_list(p) for p in poses], generator="tests/golden/make_golden.py",
                     reference="oracle/_ref libhashdag_ref (unmodified /root/reference/src, sm_100a, default -fmad)")
         np.savez_compressed(os.path.join(out_dir, f"ref_{name}.npz"), meta=json.dumps(meta), **arrays)
 

@@ -18,6 +18,7 @@ RECIPES = {
 }
 W = H = 256
 FOG = 4.0
+UNCOMPRESSED_RECIPES = ("d12",)   # fixtures that also hold the uncompressed-colours and colour-error views (basic_dag.h:122-242)
 
 
 def recipe_scene(name, uncompressed=False):
@@ -42,6 +43,24 @@ def pose_to_list(p):
 
 def pose_from_list(l):
     return camera.CameraView(tuple(l[0]), tuple(tuple(r) for r in l[1]))
+
+
+def render_uncompressed_views(impl, scene, pose, paths, tracer_objs=None):
+    """-> (uncompressed colours, colour-error view) of a BasicDAG for the paths frame `paths`, oracle or CUDA product."""
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    if impl == "oracle":
+        from oracle import hdo
+        d = hdo.make_dag(scene, hdo.DAG_BASIC)
+        return (hdo.trace_colors(d, hdo.make_colors(scene, hdo.COLORS_UNCOMPRESSED), paths)[0],
+                hdo.trace_colors(d, hdo.make_colors(scene, hdo.COLORS_ERRORS), paths)[0])
+    from hashdag_b200 import tracer
+    t, dag, comp = tracer_objs
+    unc = tracer.BasicDAGUncompressedColors.from_scene(scene)
+    t.resolve_paths(pose, info, dag)
+    t.resolve_colors(dag, unc)
+    u = t.read_colors()
+    t.resolve_colors(dag, tracer.BasicDAGColorErrors(comp, unc))
+    return u, t.read_colors()
 
 
 def render(impl, scene, kind, pose, fog, tracer_objs=None):
@@ -80,7 +99,8 @@ def channel_diff(a, b):
 def check_golden(path, impl="oracle"):
     z = np.load(path)
     meta = json.loads(str(z["meta"]))
-    scene = recipe_scene(meta["recipe"])
+    with_unc = bool(meta.get("uncompressed_views"))
+    scene = recipe_scene(meta["recipe"], uncompressed=with_unc)
     assert scene.n_voxels == meta["n_voxels"] and scene.basic.size == meta["basic_words"], "scene builder drifted from the fixture"
     kinds = ["basic"] + (["hash"] if meta["has_hash_colors"] else [])
     objs = {}
@@ -100,3 +120,7 @@ def check_golden(path, impl="oracle"):
             assert np.array_equal(s, z[f"shadows_{i}"]), f"pose {i} {kind}: shaded frame differs"
             # fog goes through exp()/pow(): libm vs CUDA may differ in the last ulp -> <= 1/255
             assert channel_diff(f, z[f"fog_{i}"]) <= 1, f"pose {i} {kind}: fogged frame differs by more than 1/255"
+            if kind == "basic" and with_unc:
+                u, e = render_uncompressed_views(impl, scene, pose, p, objs.get("basic"))
+                assert np.array_equal(u, z[f"uncompressed_{i}"]), f"pose {i}: uncompressed colours differ from the reference"
+                assert np.array_equal(e, z[f"errors_{i}"]), f"pose {i}: colour-error view differs from the reference"

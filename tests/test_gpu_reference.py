@@ -15,11 +15,12 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", list(gu.RECIPES))
 def test_reference_vs_oracle_vs_product(name):
     from hashdag_b200 import tracer
-    scene = gu.recipe_scene(name)
+    with_unc = name in gu.UNCOMPRESSED_RECIPES
+    scene = gu.recipe_scene(name, uncompressed=with_unc)
     if not ref.available(scene.levels, gu.W, gu.H):
         pytest.skip("oracle/_ref variant not built")
     info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
-    rt = ref.shared(scene, gu.W, gu.H, name)
+    rt = ref.shared(scene, gu.W, gu.H, name, with_uncompressed=with_unc)
     # the reference's own BasicDAG -> HashDAG conversion reproduces our packer bit for bit
     pool, pt, first, top = rt.hash_dag()
     assert first == scene.hash_first_node_index and top == scene.hash_pool_top
@@ -52,6 +53,20 @@ def test_reference_vs_oracle_vs_product(name):
                 assert np.array_equal(c, rc), f"{tag}: {(c != rc).sum()} colour pixels differ"
                 assert np.array_equal(s, rs), f"{tag}: {(s != rs).sum()} shaded pixels differ"
                 assert gu.channel_diff(f, rf) <= 1, f"{tag}: fog differs by more than 1/255"
+        if with_unc:
+            # BasicDAGUncompressedColors and BasicDAGColorErrors (basic_dag.h:122-242, instantiated at tracer.cu:705-711):
+            # the reference's kernels against oracle and product
+            rt.resolve_paths(0, pose, info)
+            rp = rt.read_paths()
+            rt.resolve_colors(0, 0)
+            ru = rt.read_colors()
+            rt.resolve_colors(0, 2)
+            re_ = rt.read_colors()
+            assert (ru != rc).any() and (re_ == 0xFFFFFFFF).any() and (re_ == 0xFF000000).any(), "the two views show nothing"
+            for impl in ("oracle", "cuda"):
+                u, e = gu.render_uncompressed_views(impl, scene, pose, rp, objs["basic"])
+                assert np.array_equal(u, ru), f"{name} pose {i} {impl}: {(u != ru).sum()} uncompressed-colour pixels differ from the reference"
+                assert np.array_equal(e, re_), f"{name} pose {i} {impl}: {(e != re_).sum()} colour-error pixels differ from the reference"
     t.close()
 
 
