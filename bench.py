@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-fused", "nccl"],
                     help="N > 1: how the tiles reach rank 0's frame -- stored over peer memory by a scatter kernel (default), by the shadows kernel "
                          "itself (peer-fused, HDT_OPT_EXCHANGE_FUSED), or NCCL gather + assembly (A/B)")
+    ap.add_argument("--e2e-exchange", default="host", choices=["host", "rank0"],
+                    help="N > 1, end-to-end loop: how the frame reaches host memory -- every rank stores its tiles into pinned host memory shared by "
+                         "the ranks over its own PCIe link (hdt_exchange_attach_host, default), or rank 0 copies the frame assembled in its device memory (A/B)")
     ap.add_argument("--frames-in-flight", type=int, default=3, choices=[1, 2, 3, 4],
                     help="tracer contexts (each with its own streams and frame buffers) the fly-through alternates between")
     return ap.parse_args()
@@ -483,12 +486,49 @@ def run_ours(args):
     for t_ in lanes:
         t_.set_option(tracer.OPT_BEAM_PREFETCH, 0)
     host_frames = [host_frame] + [torch.empty(W * H, dtype=torch.int32).pin_memory() for _ in lanes[1:]] if rank == 0 else None
+    host_lanes, host_shm, host_views = [], [], []
+    if world > 1 and args.e2e_exchange == "host" and not os.environ.get("HDT_BENCH_NO_GATHER"):
+        # N > 1: two more contexts per rank whose exchange block is pinned HOST memory shared by all ranks (POSIX shared memory):
+        # every rank pushes its own tiles over its own PCIe link, nothing funnels through rank 0's GPU
+        from multiprocessing import shared_memory
+        for _ in range(2):
+            t_ = tracer.DAGTracer(True, W, H, args.levels, device=local_rank)
+            t_.set_partition(rank, world, tile_log2)
+            nbytes = t_.exchange_block_bytes()
+            box = [None]
+            if rank == 0:
+                shm = shared_memory.SharedMemory(create=True, size=nbytes)      # zero-filled
+                box = [shm.name]
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                shm = shared_memory.SharedMemory(name=box[0])
+            view = np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)
+            t_.exchange_attach_host(view.ctypes.data, nbytes)
+            host_lanes.append(t_); host_shm.append(shm); host_views.append(view)
+        dist.barrier()
+        for i in range(2):          # warm-up: first touch of the mapped pages, one frame per lane
+            host_lanes[i].enqueue_frame(params[i], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+            host_lanes[i].exchange_frame()
+        for t_ in host_lanes:
+            t_.sync()
+            if rank == 0:
+                t_.exchange_release()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         p = poses[(args.warmup + i) % len(poses)]
         k = i % len(lanes)
-        if world == 1:
+        if host_lanes:
+            # frame i: kernels -> tiles stored into the shared host frame of lane k (+ arrival flags); a lane is synchronised -- on
+            # rank 0 that means the whole frame is in host memory -- and released before it is given the next frame
+            k = i % 2
+            if i >= 2:
+                host_lanes[k].sync()
+                if rank == 0:
+                    host_lanes[k].exchange_release()
+            host_lanes[k].enqueue_frame(camera.trace_params(p, info, args.levels, W, H), dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+            host_lanes[k].exchange_frame()
+        elif world == 1:
             if i >= len(lanes):
                 lanes[k].sync()
             lanes[k].enqueue_frame(camera.trace_params(p, info, args.levels, W, H), dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True,
@@ -507,6 +547,8 @@ def run_ours(args):
                 if peer:
                     lanes[k].exchange_release()          # after the copy on the same stream: the peers may overwrite frame k
     sync_all()
+    for t_ in host_lanes:
+        t_.sync()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     if world > 1:
@@ -586,6 +628,34 @@ def run_ours(args):
             whole.close()
         barrier()
 
+    host_mismatch = None
+    if host_lanes:
+        # the frame assembled in shared host memory against the same frame rendered whole on rank 0
+        host_mismatch = 0
+        if rank == 0:
+            for t_ in host_lanes:
+                t_.exchange_release()
+        whole = tracer.DAGTracer(True, W, H, args.levels, device=local_rank) if rank == 0 else None
+        for i in sample_ids[:2]:
+            host_lanes[0].enqueue_frame(params[i], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
+            host_lanes[0].exchange_frame()
+            host_lanes[0].sync()
+            if rank == 0:
+                got = host_views[0][: W * H * 4].view(np.uint32).reshape(H, W).copy()
+                host_lanes[0].exchange_release()
+                whole.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
+                host_mismatch += int((whole.read_colors() != got).sum())
+        if whole is not None:
+            whole.close()
+        barrier()
+        for t_ in host_lanes:
+            t_.close()
+        del host_views[:]
+        for shm in host_shm:
+            shm.close()
+            if rank == 0:
+                shm.unlink()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -609,6 +679,9 @@ def run_ours(args):
     }
     if exchange_mismatch is not None:
         out["parity_check_mismatched_pixels_vs_whole_frame_on_rank0"] = exchange_mismatch
+    if host_mismatch is not None:
+        out["parity_check_mismatched_pixels_host_frame_vs_whole_frame_on_rank0"] = host_mismatch
+        out["e2e"]["path"] = "every rank stores its tiles into pinned host memory shared by the ranks (hdt_exchange_attach_host), two frames in flight"
     if single_ms:
         single_value = rays / (single_ms * 1e-3 * args.steps) / 1e6
         out["single_gpu_same_workload"] = {"ms_per_step": single_ms, "value": single_value, "unit": UNIT, "frames_in_flight": 3,
@@ -776,6 +849,10 @@ def main():
         run_reference_cuda(args)
     else:
         run_ours(args)
+    # ONE JSON line on stdout: whatever native libraries print while the process winds down (the reference's memory tracker
+    # reports "No leaks!" from a static destructor) goes to stderr
+    sys.stdout.flush()
+    os.dup2(2, 1)
 
 
 if __name__ == "__main__":

@@ -17,9 +17,11 @@ using u32 = uint32_t;
 using u64 = uint64_t;
 
 // Any-hit walks (trace_shadows) may visit children in any order -- the result is "is there a voxel", not which one.
-// 0: highest child first like the reference (tracer.cu:493); 1: lowest child first (= front to back for the sun's direction).
+// 0: highest child first like the reference (tracer.cu:493); 1: lowest child first (= front to back for the sun's direction,
+// whose components are all positive: occluders near the surface point are met first).  A/B on B200, 1080p depth 17
+// (profiles/r2_ab.md): shadows pass 0.328 ms against 0.346 ms, frames identical.
 #ifndef HDT_ANYHIT_LOW_FIRST
-#define HDT_ANYHIT_LOW_FIRST 0
+#define HDT_ANYHIT_LOW_FIRST 1
 #endif
 constexpr u32 kMaxLevels = 24;   // float node centres stay exact below 2^24
 constexpr u32 kPageWords = 512;  // C_pageSize, hash_dag_globals.h:10

@@ -7,8 +7,15 @@
 // the frame has been consumed, publishes a credit the peers wait for before overwriting the buffer.  No SM of the root
 // moves any pixel of the other ranks, and nothing synchronises with the host.
 //
-//   exchange block (root's device memory):  [ frame u32[W*H] | pad | arrivals u32 | credit u32 ]
-//   lane sequence numbers start at 1:  arrivals target = (world-1) * seq,  credit published = seq,  peers wait credit >= seq-1
+//   exchange block (root's device memory, or pinned host memory shared by all processes):
+//       [ frame u32[W*H] | pad | credit u32 | pad | arrived u32[64] ]
+//   lane sequence numbers start at 1:  rank r stores arrived[r] = seq once its tiles of frame seq are in place (a plain store
+//   behind a system-scope fence: idempotent, needs no atomics, so the block may as well live in host memory), the root waits
+//   for arrived[1 .. world-1] >= seq, publishes credit = seq when the frame has been consumed; peers wait credit >= seq-1.
+//
+// With the block in pinned, mapped HOST memory shared by all ranks (hdt_exchange_attach_host) the same kernels make every
+// rank push its own tiles over its own PCIe link: the assembled frame materialises in host memory without passing through
+// rank 0's GPU or its single link.
 #pragma once
 #include "hdt_device.cuh"
 
@@ -16,25 +23,29 @@ namespace hdt {
 
 // What a fused final pass needs: rank 0's frame (nullptr = not fused), this context's last-CTA counter, and rank 0's
 // arrival counter (nullptr on rank 0 itself, which does not signal).
-struct ExchangeOut { u32* frame; u32* ctasDone; u32* arrivals; };
+struct ExchangeOut { u32* frame; u32* ctasDone; u32* arrived; u32 seq; };
 
-struct ExchangeCounters { u32 arrivals; u32 credit; u32 pad[62]; };   // 256 B, lives behind the frame
+constexpr u32 kMaxExchangeRanks = 64;
+struct ExchangeCounters { u32 credit; u32 pad[63]; u32 arrived[kMaxExchangeRanks]; };   // 512 B, lives behind the frame
 
 __device__ __forceinline__ u32 load_volatile(const u32* p) { return *reinterpret_cast<const volatile u32*>(p); }
 
-// One thread: wait until *counter - target >= 0 (wrap-safe).  After maxCycles SM cycles (0 = wait for ever; default
+// One thread: wait until words[i] - target >= 0 (wrap-safe) for every i < nWords.  After maxCycles SM cycles (0 = wait for ever; default
 // ~20 s, HDT_OPT_EXCHANGE_TIMEOUT_MS) it gives up: *timedOut (host-mapped) is raised, so a lost peer shows up as an error
 // at the next host-synchronising call instead of a hung box, and *abortFlag (device) makes the kernels queued behind it
 // skip their stores and signals -- a frame that timed out is dropped, never half-written over one still being read.
-__global__ void exchange_wait_kernel(const u32* counter, u32 target, unsigned long long maxCycles, u32* timedOut, u32* abortFlag)
+__global__ void exchange_wait_kernel(const u32* words, u32 nWords, u32 target, unsigned long long maxCycles, u32* timedOut, u32* abortFlag)
 {
     const long long t0 = clock64();
-    while (int(load_volatile(counter) - target) < 0) {
-        __nanosleep(100);
-        if (maxCycles && (unsigned long long)(clock64() - t0) > maxCycles) {
-            *reinterpret_cast<volatile u32*>(timedOut) = 1;
-            *reinterpret_cast<volatile u32*>(abortFlag) = 1;
-            break;
+    for (u32 i = 0; i < nWords; ++i) {
+        while (int(load_volatile(words + i) - target) < 0) {
+            __nanosleep(100);
+            if (maxCycles && (unsigned long long)(clock64() - t0) > maxCycles) {
+                *reinterpret_cast<volatile u32*>(timedOut) = 1;
+                *reinterpret_cast<volatile u32*>(abortFlag) = 1;
+                i = nWords;
+                break;
+            }
         }
     }
     __threadfence_system();
@@ -46,16 +57,16 @@ __global__ void exchange_publish_kernel(u32* counter, u32 value)
     *reinterpret_cast<volatile u32*>(counter) = value;
 }
 
-__global__ void exchange_signal_kernel(u32* arrivals, const u32* abortFlag)   // a rank that owns no tile still has to arrive
+__global__ void exchange_signal_kernel(u32* arrived, u32 seq, const u32* abortFlag)   // a rank that owns no tile still has to arrive
 {
     if (load_volatile(abortFlag)) return;
     __threadfence_system();
-    atomicAdd_system(arrivals, 1u);
+    *reinterpret_cast<volatile u32*>(arrived) = seq;
 }
 
-// End of a kernel that stored into rank 0's frame: make the CTA's stores visible system-wide, count the CTA, and let the
-// last one bump `arrivals` in rank 0's memory.  Every thread of the CTA must call it.
-__device__ __forceinline__ void exchange_signal_last_cta(u32* __restrict__ ctasDone, u32* arrivals)
+// End of a kernel that stored into the shared frame: make the CTA's stores visible system-wide, count the CTA, and let the
+// last one publish arrived[rank] = seq.  Every thread of the CTA must call it.
+__device__ __forceinline__ void exchange_signal_last_cta(u32* __restrict__ ctasDone, u32* arrived, u32 seq)
 {
     __threadfence_system();
     __syncthreads();
@@ -64,7 +75,7 @@ __device__ __forceinline__ void exchange_signal_last_cta(u32* __restrict__ ctasD
         if (prev == gridDim.x - 1) {
             *ctasDone = 0;                            // ready for the next launch (stream order separates launches)
             __threadfence_system();
-            if (arrivals) atomicAdd_system(arrivals, 1u);
+            if (arrived) *reinterpret_cast<volatile u32*>(arrived) = seq;
         }
     }
 }
@@ -72,7 +83,7 @@ __device__ __forceinline__ void exchange_signal_last_cta(u32* __restrict__ ctasD
 // This rank's compact tiles (each (1<<tileLog2)^2 pixels, row-major, owned tiles back to back) -> the row-major frame,
 // which may live in another GPU's memory.  One CTA per 16 tile rows; the last CTA to finish signals `arrivals`.
 __global__ void __launch_bounds__(256) exchange_scatter_kernel(const u32* __restrict__ compact, u32* __restrict__ frame, const PixelMap map,
-                                                                u32* __restrict__ ctasDone, u32* arrivals, const u32* abortFlag)
+                                                                u32* __restrict__ ctasDone, u32* arrived, u32 seq, const u32* abortFlag)
 {
     if (load_volatile(abortFlag)) return;             // the wait in front of this launch gave up: drop the frame
     const u32 T = 1u << map.tileLog2, rowsPerCta = 16, ctasPerTile = T / rowsPerCta;
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const u32* __rest
             if (y < map.height && x < map.width) frame[u64(y) * map.width + x] = src[r * T + c];
         }
     }
-    exchange_signal_last_cta(ctasDone, arrivals);
+    exchange_signal_last_cta(ctasDone, arrived, seq);
 }
 
 }  // namespace hdt

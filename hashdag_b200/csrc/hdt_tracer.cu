@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kBlockThreads, HDT_MIN_BLOCKS_SHADOWS) trace_s
     if (thread_pixel(map, x, y)) shadow_pixel<DAG>(cam, sp, dag, levels, map, paths, origins, colors, tab, bs, status, x, y, xo.frame);
     // Fused framebuffer exchange (hdt_exchange.cuh): the pixel above also went into rank 0's row-major frame; the last CTA
     // of the launch tells rank 0 that this rank's tiles are complete.
-    if (xo.frame) exchange_signal_last_cta(xo.ctasDone, xo.arrivals);
+    if (xo.frame) exchange_signal_last_cta(xo.ctasDone, xo.arrived, xo.seq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,6 +501,8 @@ struct hdt_ctx {
     // framebuffer exchange over peer memory (hdt_exchange.cuh)
     u32* xBlock = nullptr;              // [frame W*H][ExchangeCounters]: own allocation (root) or a mapping of the root's
     bool xOwned = false, xIpc = false;
+    void* xHostBlock = nullptr;         // hdt_exchange_attach_host: the pinned host block xBlock aliases (unregistered at destroy if this context registered it)
+    bool xHostRegistered = false;
     u32 xSeq = 0;                       // frames exchanged on this context
     bool xFused = false;                // HDT_OPT_EXCHANGE_FUSED: shadow passes store into rank 0's frame themselves
     u32 xFusedSeq = 0;                  // sequence number the last fused shadow pass stored for
@@ -519,6 +521,8 @@ struct hdt_ctx {
     const u32* ancForPool = nullptr; const u32* ancForPrefix = nullptr; u32 ancForRoot = 0;
     u32* physToVirt = nullptr;          // hdt_hash_dag_resolve: physical page -> virtual page (grow-only)
     size_t physToVirtPages = 0;
+    void* comm = nullptr;               // ncclComm_t (hdt_comm_init, hdt_multi.cuh); null while world == 1
+    u32 commRank = 0, commWorld = 1;
     void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, per-macro-block sums (grow-only)
     size_t rebuildScratchBytes = 0;
 
@@ -813,17 +817,17 @@ int finish_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const S
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     HDT_CUDA(cudaStreamWaitEvent(c->stream, c->beamSerial ? c->join[1] : c->setupDone[1], 0));   // the origins
     // Fused framebuffer exchange: this pass writes the final colours, so it can store them into rank 0's frame itself.
-    ExchangeOut xo{ nullptr, nullptr, nullptr };
+    ExchangeOut xo{ nullptr, nullptr, nullptr, 0 };
     if (c->xFused && c->xBlock) {
-        if (c->xFusedSeq == c->xSeq + 1)
-            return fail(HDT_ERR_STATE, "fused framebuffer exchange: a second shadows pass before hdt_exchange_frame (every fused shadows pass must be followed by one)");
+        // arrived[rank] = seq is a plain store: a shadows pass repeated before hdt_exchange_frame (a re-render, a standalone
+        // hdt_resolve_shadows) stores the same frame number again and cannot run the root ahead
         const u32 seq = c->xSeq + 1;
         ExchangeCounters* k = reinterpret_cast<ExchangeCounters*>(reinterpret_cast<char*>(c->xBlock) + ((size_t(c->map.width) * c->map.height * 4 + 255) & ~size_t(255)));
         if (c->map.rank != 0) {   // rank 0 must have consumed the previous frame of this lane
-            exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, c->xWaitCycles, c->xTimedOutDev, c->xCtasDone + 1);
+            exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, 1, seq - 1, c->xWaitCycles, c->xTimedOutDev, c->xCtasDone + 1);
             HDT_LAUNCHED("exchange_wait_kernel");
         }
-        xo = ExchangeOut{ c->xBlock, c->xCtasDone, c->map.rank != 0 ? &k->arrivals : nullptr };
+        xo = ExchangeOut{ c->xBlock, c->xCtasDone, c->map.rank != 0 ? &k->arrived[c->map.rank] : nullptr, seq };
         c->xFusedSeq = seq;
     }
     if (d.has_prefix()) trace_shadows_kernel<HashDagPrefixDev><<<grid, block, 0, c->stream>>>(cam, sp, d.prefixed(), c->levels, c->map, c->paths, c->ray_planes(1), c->colors, c->tables, prep.beams, prep.tag, xo);
@@ -936,8 +940,10 @@ int hdt_destroy(hdt_ctx* c)
     cudaFree(c->tables);
     if (c->xBlock && c->xOwned) cudaFree(c->xBlock);
     if (c->xBlock && c->xIpc) cudaIpcCloseMemHandle(c->xBlock);
+    if (c->xHostBlock && c->xHostRegistered) cudaHostUnregister(c->xHostBlock);
     cudaFree(c->xCtasDone);
     if (c->xTimedOut) cudaFreeHost(c->xTimedOut);
+    hdt_comm_destroy(c);
     cudaFree(c->physToVirt);
     cudaFree(c->rebuildScratch);
     if (c->stagingHost) cudaFreeHost(c->stagingHost);
@@ -1261,6 +1267,7 @@ size_t exchange_frame_bytes(const hdt_ctx* c) { return (size_t(c->map.width) * c
 ExchangeCounters* exchange_counters(const hdt_ctx* c) { return reinterpret_cast<ExchangeCounters*>(reinterpret_cast<char*>(c->xBlock) + exchange_frame_bytes(c)); }
 int exchange_common(hdt_ctx* c)
 {
+    if (c->map.world > kMaxExchangeRanks) return fail(HDT_ERR_ARG, "framebuffer exchange: at most 64 ranks");
     if (!c->xCtasDone) {
         HDT_CUDA(cudaMalloc(&c->xCtasDone, 2 * sizeof(u32)));
         HDT_CUDA(cudaMemset(c->xCtasDone, 0, 2 * sizeof(u32)));
@@ -1329,6 +1336,31 @@ int hdt_exchange_attach(hdt_ctx* c, void* block_dev)
     return exchange_common(c);
 }
 
+int hdt_exchange_block_bytes(hdt_ctx* c, uint64_t* bytes)
+{
+    if (!c || !bytes) return fail(HDT_ERR_ARG, "null argument");
+    *bytes = exchange_frame_bytes(c) + sizeof(ExchangeCounters);
+    return HDT_OK;
+}
+
+int hdt_exchange_attach_host(hdt_ctx* c, void* host_block, uint64_t bytes)
+{
+    if (!c || !host_block) return fail(HDT_ERR_ARG, "null argument");
+    if (c->xBlock) return fail(HDT_ERR_STATE, "hdt_exchange_attach_host: the context already has an exchange");
+    if (bytes < exchange_frame_bytes(c) + sizeof(ExchangeCounters)) return fail(HDT_ERR_CAPACITY, "hdt_exchange_attach_host: block smaller than hdt_exchange_block_bytes");
+    HDT_CUDA(cudaSetDevice(c->device));
+    // pin + map the caller's (shared) memory; a second context of this process finds it registered already
+    cudaError_t e = cudaHostRegister(host_block, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();
+    else if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister(exchange block)");
+    else c->xHostRegistered = true;
+    void* dev = nullptr;
+    HDT_CUDA(cudaHostGetDevicePointer(&dev, host_block, 0));
+    c->xBlock = static_cast<u32*>(dev);
+    c->xHostBlock = host_block;
+    return exchange_common(c);
+}
+
 int hdt_exchange_frame(hdt_ctx* c)
 {
     if (!c) return fail(HDT_ERR_ARG, "null context");
@@ -1343,18 +1375,18 @@ int hdt_exchange_frame(hdt_ctx* c)
     const bool root = c->map.rank == 0;
     u32* abortDev = c->xCtasDone + 1;
     if (!root && !fused) {   // the root must have consumed the previous frame of this lane before it is overwritten
-        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, seq - 1, c->xWaitCycles, timedOutDev, abortDev);
+        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, 1, seq - 1, c->xWaitCycles, timedOutDev, abortDev);
         HDT_LAUNCHED("exchange_wait_kernel");
     }
     if (grid) {
-        exchange_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->colors, c->xBlock, c->map, c->xCtasDone, root ? nullptr : &k->arrivals, abortDev);
+        exchange_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->colors, c->xBlock, c->map, c->xCtasDone, root ? nullptr : &k->arrived[c->map.rank], seq, abortDev);
         HDT_LAUNCHED("exchange_scatter_kernel");
     } else if (!root && !fused) {
-        exchange_signal_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals, abortDev);
+        exchange_signal_kernel<<<1, 1, 0, c->stream>>>(&k->arrived[c->map.rank], seq, abortDev);
         HDT_LAUNCHED("exchange_signal_kernel");
     }
     if (root && c->map.world > 1) {
-        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->arrivals, (c->map.world - 1) * seq, c->xWaitCycles, timedOutDev, abortDev);
+        exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->arrived[1], c->map.world - 1, seq, c->xWaitCycles, timedOutDev, abortDev);
         HDT_LAUNCHED("exchange_wait_kernel");
     }
     return HDT_OK;
@@ -1631,3 +1663,5 @@ int hdt_is_empty(hdt_ctx* c, int dag_kind, const void* dag_pod, size_t dag_pod_s
 }
 
 }  // extern "C"
+
+#include "hdt_multi.cuh"

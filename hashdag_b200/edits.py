@@ -270,7 +270,9 @@ class HashDagReplica:
     """One GPU's copy of a HashDAG (+ colours) that follows edits through deltas.  Needs CUDA."""
 
     def __init__(self, tracer_obj, pool, page_table, pool_top, first_node_index, levels, pool_capacity_pages,
-                 color_nodes=None, color_offsets=None, main_leaf=None, color_node_capacity=0, device="cuda:0", resolved=True):
+                 color_nodes=None, color_offsets=None, main_leaf=None, color_node_capacity=0, device="cuda:0", resolved=True, replicate_from=None):
+        """replicate_from = r (tracer with a communicator): rank r's arrays are the truth -- the other ranks pass arrays of
+        the same SIZES (contents ignored) and receive rank r's over hdt_replicate (initial replication)."""
         import torch
         from . import tracer as T
         self._T, self._torch, self.tracer, self.device, self.levels = T, torch, tracer_obj, device, levels
@@ -279,6 +281,11 @@ class HashDagReplica:
         self.pool[: pool.size] = T._to_device(pool, device)
         self.page_table = T._to_device(page_table, device)
         self.pool_top, self.first_node_index = int(pool_top), int(first_node_index)
+        if replicate_from is not None and tracer_obj.comm_world > 1:
+            torch.cuda.synchronize()
+            tracer_obj.replicate(self.pool[: int(pool_top) * 512], replicate_from)
+            tracer_obj.replicate(self.page_table, replicate_from)
+            tracer_obj.sync()
         # the resolved pool (child pointers pre-translated, csrc/hdt_resolve.cuh) follows every edit page by page
         # ... and so does the prefix pool (voxels under a node's earlier children: trace_colors without the DAG walk)
         self.resolved_pool = self.prefix_pool = None
@@ -296,62 +303,112 @@ class HashDagReplica:
             self.n_color_nodes = int(color_nodes.size)
             self.color_offsets = T._to_device(color_offsets, device)
             self.main_leaf = main_leaf                  # tracer.CompressedColorLeaf on this device
+            if replicate_from is not None and tracer_obj.comm_world > 1:
+                torch.cuda.synchronize()
+                for tns in (self.color_nodes[: self.n_color_nodes], self.color_offsets, main_leaf.weights, main_leaf.blocks, main_leaf.macro_blocks):
+                    if tns is not None and tns.numel():
+                        tracer_obj.replicate(tns, replicate_from)
+                tracer_obj.sync()
             self.leaves = {}                            # index -> tracer.CompressedColorLeaf (keeps the tensors alive)
             self.leaf_pods = None                       # int64 tensor, 13 words per leaf (CompressedColorLeaf, 104 B)
             self._pods_host = None                      # the same on the host, updated row by row
 
-    def apply(self, delta: DagDelta) -> None:
-        """Enqueue the delta on the tracer's stream (hdt_apply_ranges_host: staged through pinned memory, no host
-        synchronisation for the pool / page table / colour tree); new colour leaves go up as ONE packed buffer."""
+    def _replica_pod(self):
+        T = self._T
+        return T.ReplicaPod(self.pool.data_ptr(), self.pool.numel(), self.page_table.data_ptr(), self.page_table.numel(), self.first_node_index, self.pool_top,
+                            T._ptr(self.resolved_pool), T._ptr(self.prefix_pool))
+
+    def apply(self, delta: "DagDelta | None", root: int = 0, pod=None) -> None:
+        """One edit on this rank's replica, through the C ABI's multi-GPU layer (hdt_broadcast_dirty / hdt_broadcast_ranges /
+        hdt_replicate, csrc/hdt_multi.cuh): rank `root` passes the delta (and optionally `pod`, the hdt_dag_delta a
+        tracer.DirtyTracker built, handed over without a copy), the other ranks None.  Everything is enqueued on the
+        tracer's stream; with one rank no communicator is involved."""
         T, torch = self._T, self._torch
-        if int(delta.pool_top) * 512 > self.pool.numel():
-            raise T.TracerError("HashDagReplica: the edit outgrew the replica's pool capacity")
-        self.tracer.apply_ranges_host(self.pool, delta.pool_payload, delta.pool_ranges)
-        self.tracer.apply_ranges_host(self.page_table, delta.table_payload, delta.table_ranges)
-        self.pool_top, self.first_node_index = int(delta.pool_top), int(delta.first_node_index)
-        if self.resolved_pool is not None and len(delta.pool_ranges):
-            # pages whose words changed, plus nothing else: older nodes never point at newer ones and their pointers stay valid
-            self.tracer.resolve_hash_dag(self._hash_dag(), self.resolved_pool, delta.pool_ranges, self.prefix_pool)
-        if self.has_colors and delta.n_color_nodes:
-            if delta.n_color_nodes > self.color_nodes.numel():
-                grown = torch.zeros(2 * delta.n_color_nodes, dtype=torch.int32, device=self.device)
-                self.tracer.sync()
+        tr = self.tracer
+        is_root = tr.comm_rank == root
+        multi = tr.comm_world > 1
+        keep = None
+        if is_root and pod is None:
+            pod, keep = T.delta_pod_from_arrays(delta.first_node_index, delta.pool_top, delta.pool_ranges, delta.pool_payload, delta.table_ranges, delta.table_payload)
+        rp = self._replica_pod()
+        tr.broadcast_dirty(rp, pod if is_root else None, root)          # pool, page table, resolved + prefix pools
+        self.pool_top, self.first_node_index = int(rp.pool_top), int(rp.first_node_index)
+        del keep
+        if not self.has_colors:
+            return
+        # colour tree + rebuilt unique leaves: sizes first (ranks other than root learn them here), then spans, then ONE packed leaf buffer
+        ids, offs, flat = [], [], None
+        if is_root:
+            ids = sorted(delta.color_leaves)
+            parts, total = [], 0
+            for i in ids:
+                l = delta.color_leaves[i]
+                for a in (l.blocks, l.macro_blocks, l.weights):          # 8-byte arrays first: every part stays aligned
+                    bts = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+                    offs.append((total, a.size))
+                    parts.append(bts)
+                    total += (bts.size + 7) // 8 * 8
+            flat = np.zeros(total, dtype=np.uint8)
+            for (o, _), bts in zip(offs, parts):
+                flat[o:o + bts.size] = bts
+        n_nodes = delta.n_color_nodes if is_root else 0
+        n_leaves = delta.n_color_leaves if is_root else 0
+        if multi:
+            # [n_color_nodes, n_color_leaves, n_ids, blob_bytes, then per id: id, 3 x (offset, count)]  -- two hdt_replicate calls
+            head = np.zeros(4, dtype=np.int64)
+            meta = np.zeros(0, dtype=np.int64)
+            if is_root:
+                meta = np.array([v for k, i in enumerate(ids) for v in (i, *offs[3 * k], *offs[3 * k + 1], *offs[3 * k + 2])], dtype=np.int64)
+                head[:] = (n_nodes, n_leaves, len(ids), flat.size)
+            th = torch.from_numpy(head).to(self.device)
+            torch.cuda.current_stream().synchronize()
+            tr.replicate(th, root)
+            tr.sync()
+            n_nodes, n_leaves, n_ids, blob_bytes = (int(v) for v in th.cpu().tolist())
+            if n_ids:
+                tm = torch.from_numpy(meta).to(self.device) if is_root else torch.empty(7 * n_ids, dtype=torch.int64, device=self.device)
+                torch.cuda.current_stream().synchronize()
+                tr.replicate(tm, root)
+                tr.sync()
+                m = tm.cpu().numpy().reshape(n_ids, 7)
+                ids = [int(v) for v in m[:, 0]]
+                offs = [(int(m[k, 1 + 2 * j]), int(m[k, 2 + 2 * j])) for k in range(n_ids) for j in range(3)]
+        if n_nodes:
+            if n_nodes > self.color_nodes.numel():
+                grown = torch.zeros(2 * n_nodes, dtype=torch.int32, device=self.device)
+                tr.sync()
                 grown[: self.color_nodes.numel()] = self.color_nodes
                 torch.cuda.synchronize()
                 self.color_nodes = grown
-            self.tracer.apply_ranges_host(self.color_nodes, delta.color_node_payload, delta.color_node_ranges)
-            self.n_color_nodes = delta.n_color_nodes
-            if delta.color_leaves:
-                # one packed upload for every new / rebuilt leaf of this edit; the leaves are views into it
-                ids = sorted(delta.color_leaves)
-                parts, offs, total = [], [], 0
-                for i in ids:
-                    l = delta.color_leaves[i]
-                    for a in (l.blocks, l.macro_blocks, l.weights):          # 8-byte arrays first: every part stays aligned
-                        b = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-                        offs.append((total, a.size))
-                        parts.append(b)
-                        total += (b.size + 7) // 8 * 8
-                flat = np.zeros(total, dtype=np.uint8)
-                for (o, _), b in zip(offs, parts):
-                    flat[o:o + b.size] = b
-                buf = torch.from_numpy(flat).to(self.device)
+            if is_root:
+                tr.broadcast_ranges(self.color_nodes, delta.color_node_payload, delta.color_node_ranges, root)
+            else:
+                tr.broadcast_ranges(self.color_nodes, None, None, root)
+            self.n_color_nodes = n_nodes
+            if ids:
+                if is_root:
+                    buf = torch.from_numpy(flat).to(self.device)
+                else:
+                    buf = torch.empty(blob_bytes, dtype=torch.uint8, device=self.device)
+                if multi:
+                    torch.cuda.current_stream().synchronize()
+                    tr.replicate(buf, root)
                 for k, i in enumerate(ids):
                     (ob, nb), (om, nm), (ow, nw) = offs[3 * k: 3 * k + 3]
                     blocks = buf[ob: ob + 8 * nb].view(torch.int64) if nb else None
                     macro = buf[om: om + 8 * nm].view(torch.int64) if nm else None
                     weights = buf[ow: ow + 4 * nw].view(torch.int32) if nw else None
                     self.leaves[i] = T.CompressedColorLeaf(weights, blocks, macro, T.UNIQUE_OFFSET)
-            if delta.n_color_leaves and (delta.color_leaves or self._pods_host is None or self._pods_host.shape[0] != delta.n_color_leaves):
-                if self._pods_host is None or self._pods_host.shape[0] < delta.n_color_leaves:
-                    grown = np.zeros((delta.n_color_leaves, 13), dtype=np.uint64)
+            if n_leaves and (ids or self._pods_host is None or self._pods_host.shape[0] != n_leaves):
+                if self._pods_host is None or self._pods_host.shape[0] < n_leaves:
+                    grown = np.zeros((n_leaves, 13), dtype=np.uint64)
                     if self._pods_host is not None:
                         grown[: self._pods_host.shape[0]] = self._pods_host
                     self._pods_host = grown
-                for i in delta.color_leaves:
+                for i in ids:
                     self._pods_host[i] = np.frombuffer(self.leaves[i].pod(), dtype=np.uint64)
-                self.tracer.sync()                      # frames in flight may still read the previous POD array
-                self.leaf_pods = T._to_device(self._pods_host[: delta.n_color_leaves].reshape(-1), self.device)
+                tr.sync()                               # frames in flight may still read the previous POD array
+                self.leaf_pods = T._to_device(self._pods_host[:n_leaves].reshape(-1), self.device)
 
     def _hash_dag(self):
         return self._T.HashDAG(self.pool, self.page_table, self.pool_top, self.first_node_index, self.levels)

@@ -35,14 +35,31 @@ EXPORTS = (
     "hdt_create", "hdt_destroy", "hdt_last_error", "hdt_set_partition", "hdt_set_option", "hdt_beam_stats", "hdt_pass_timeline", "hdt_resolve_paths", "hdt_resolve_colors",
     "hdt_resolve_shadows", "hdt_resolve_frame", "hdt_resolve_frame_async", "hdt_sync", "hdt_timer_begin", "hdt_timer_end",
     "hdt_count_hits", "hdt_get_path", "hdt_read_paths", "hdt_read_colors",
-    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_exchange_create", "hdt_exchange_open", "hdt_exchange_block", "hdt_exchange_attach",
-    "hdt_exchange_frame", "hdt_exchange_release", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_hash_dag_resolve", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_launch_count", "hdt_recorded_color_passes", "hdt_version",
+    "hdt_partition_buffers", "hdt_assemble_colors", "hdt_exchange_create", "hdt_exchange_open", "hdt_exchange_block", "hdt_exchange_attach", "hdt_exchange_block_bytes", "hdt_exchange_attach_host",
+    "hdt_exchange_frame", "hdt_exchange_release", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_hash_dag_resolve", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_tracker_create", "hdt_tracker_destroy", "hdt_tracker_bucket_count", "hdt_tracker_snapshot", "hdt_tracker_delta",
+    "hdt_comm_unique_id", "hdt_comm_init", "hdt_comm_destroy", "hdt_replicate", "hdt_broadcast_dirty", "hdt_broadcast_ranges",
+    "hdt_launch_count", "hdt_recorded_color_passes", "hdt_version",
 )
 ERR_CAPACITY = 4
 
 
 class TracerError(RuntimeError):
     pass
+
+
+class Range(C.Structure):     # hdt_range
+    _fields_ = [("dst_word", C.c_uint64), ("src_word", C.c_uint64), ("n_words", C.c_uint64)]
+
+
+class DagDeltaPod(C.Structure):   # hdt_dag_delta
+    _fields_ = [("first_node_index", C.c_uint32), ("pool_top", C.c_uint32),
+                ("pool_ranges", C.c_void_p), ("n_pool_ranges", C.c_uint32), ("pool_payload", C.c_void_p), ("n_pool_payload", C.c_uint64),
+                ("table_ranges", C.c_void_p), ("n_table_ranges", C.c_uint32), ("table_payload", C.c_void_p), ("n_table_payload", C.c_uint64)]
+
+
+class ReplicaPod(C.Structure):    # hdt_replica
+    _fields_ = [("pool", C.c_void_p), ("pool_capacity_words", C.c_uint64), ("page_table", C.c_void_p), ("page_table_size", C.c_uint32),
+                ("first_node_index", C.c_uint32), ("pool_top", C.c_uint32), ("resolved_pool", C.c_void_p), ("prefix_pool", C.c_void_p)]
 
 
 class ToolInfo(C.Structure):  # tracer.h:33-39
@@ -90,6 +107,8 @@ def load_library():
     lib.hdt_exchange_open.argtypes = [C.c_void_p, C.c_char_p]
     lib.hdt_exchange_block.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.hdt_exchange_attach.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hdt_exchange_block_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.hdt_exchange_attach_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.hdt_exchange_frame.argtypes = [C.c_void_p]
     lib.hdt_exchange_release.argtypes = [C.c_void_p]
     lib.hdt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -101,6 +120,18 @@ def load_library():
     u3 = C.POINTER(C.c_uint32)
     lib.hdt_get_values.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, u3, u3, C.c_void_p, fp]
     lib.hdt_is_empty.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_uint32, u3, u3, C.POINTER(C.c_int), fp]
+    lib.hdt_tracker_create.argtypes = [C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.hdt_tracker_destroy.argtypes = [C.c_void_p]
+    lib.hdt_tracker_bucket_count.argtypes = [C.c_void_p]
+    lib.hdt_tracker_bucket_count.restype = C.c_uint32
+    lib.hdt_tracker_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.hdt_tracker_delta.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(DagDeltaPod)]
+    lib.hdt_comm_unique_id.argtypes = [C.c_char_p]
+    lib.hdt_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32]
+    lib.hdt_comm_destroy.argtypes = [C.c_void_p]
+    lib.hdt_replicate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+    lib.hdt_broadcast_dirty.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(DagDeltaPod), C.POINTER(ReplicaPod)]
+    lib.hdt_broadcast_ranges.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     lib.hdt_launch_count.restype = C.c_uint64
     lib.hdt_launch_count.argtypes = [C.c_void_p]
     lib.hdt_recorded_color_passes.restype = C.c_uint64
@@ -279,6 +310,65 @@ class HashDAGColors:
         return _dyn_array(self.nodes) + leaves + _dyn_array(self.offsets) + self.main_leaf.pod() + 3 * _NULL_DYN
 
 
+class DirtyTracker:
+    """hdt_dirty_tracker: an edit's dirty spans from the hash table's bucket fill counts (host code, no GPU needed).
+    C++ twin of edits.delta_from_bucket_sizes."""
+
+    def __init__(self, levels: int):
+        self._lib = load_library()
+        self._t = C.c_void_p()
+        _check(self._lib.hdt_tracker_create(levels, C.byref(self._t)))
+        self.n_buckets = int(self._lib.hdt_tracker_bucket_count(self._t))
+
+    def close(self):
+        if getattr(self, "_t", None):
+            self._lib.hdt_tracker_destroy(self._t)
+            self._t = None
+
+    __del__ = close
+
+    def snapshot(self, bucket_sizes: np.ndarray):
+        b = np.ascontiguousarray(bucket_sizes, dtype=np.uint32)
+        _check(self._lib.hdt_tracker_snapshot(self._t, b.ctypes.data, b.size))
+
+    def delta_pod(self, bucket_sizes, cpu_pool, cpu_page_table, first_node_index, pool_top) -> DagDeltaPod:
+        """-> hdt_dag_delta whose arrays live inside the tracker until its next call (zero-copy hand-over to hdt_broadcast_dirty)."""
+        b = np.ascontiguousarray(bucket_sizes, dtype=np.uint32)
+        assert cpu_pool.dtype == np.uint32 and cpu_page_table.dtype == np.uint32 and cpu_pool.flags.c_contiguous and cpu_page_table.flags.c_contiguous
+        pod = DagDeltaPod()
+        _check(self._lib.hdt_tracker_delta(self._t, b.ctypes.data, b.size, cpu_pool.ctypes.data, cpu_page_table.ctypes.data, int(first_node_index), int(pool_top), C.byref(pod)))
+        return pod
+
+    @staticmethod
+    def arrays(pod: DagDeltaPod):
+        """numpy copies of a delta's four arrays: (pool_ranges, pool_payload, table_ranges, table_payload)."""
+        from .edits import RANGE_DTYPE
+
+        def view(ptr, n, dtype):
+            if not n:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (int(n) * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype).copy()
+        return (view(pod.pool_ranges, pod.n_pool_ranges, RANGE_DTYPE), view(pod.pool_payload, pod.n_pool_payload, np.uint32),
+                view(pod.table_ranges, pod.n_table_ranges, RANGE_DTYPE), view(pod.table_payload, pod.n_table_payload, np.uint32))
+
+
+def comm_unique_id() -> bytes:
+    """hdt_comm_unique_id (rank 0): 128 bytes for the host to hand to every rank."""
+    buf = C.create_string_buffer(128)
+    _check(load_library().hdt_comm_unique_id(buf))
+    return buf.raw
+
+
+def delta_pod_from_arrays(first_node_index, pool_top, pool_ranges, pool_payload, table_ranges, table_payload):
+    """hdt_dag_delta over numpy arrays (kept alive by the returned tuple's second element)."""
+    keep = [np.ascontiguousarray(pool_ranges), np.ascontiguousarray(pool_payload, dtype=np.uint32),
+            np.ascontiguousarray(table_ranges), np.ascontiguousarray(table_payload, dtype=np.uint32)]
+    pod = DagDeltaPod(int(first_node_index), int(pool_top), keep[0].ctypes.data, len(keep[0]), keep[1].ctypes.data, keep[1].size,
+                      keep[2].ctypes.data, len(keep[2]), keep[3].ctypes.data, keep[3].size)
+    return pod, keep
+
+
 def _d3(v):
     return (C.c_double * 3)(*[float(x) for x in v])
 
@@ -297,6 +387,7 @@ class DAGTracer:
         self._ctx = C.c_void_p()
         _check(self._lib.hdt_create(width, height, levels, device, C.byref(self._ctx)))
         self._ms = C.c_float()
+        self.comm_rank, self.comm_world = 0, 1
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -417,6 +508,16 @@ class DAGTracer:
         """Other ranks living in rank 0's process: attach by pointer (CUDA IPC cannot open a handle in its own process)."""
         _check(self._lib.hdt_exchange_attach(self._ctx, block_ptr))
 
+    def exchange_block_bytes(self) -> int:
+        n = C.c_uint64()
+        _check(self._lib.hdt_exchange_block_bytes(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    def exchange_attach_host(self, host_address: int, n_bytes: int):
+        """Every rank (rank 0 too): use zero-initialised shared HOST memory as the exchange block; tiles then travel
+        straight into host memory over each rank's own PCIe link."""
+        _check(self._lib.hdt_exchange_attach_host(self._ctx, C.c_void_p(host_address), n_bytes))
+
     def exchange_frame(self):
         """Every rank, after the frame's passes: store the owned tiles into rank 0's frame (asynchronous)."""
         _check(self._lib.hdt_exchange_frame(self._ctx))
@@ -454,6 +555,29 @@ class DAGTracer:
             rptr, n = ranges.ctypes.data, len(ranges)
         _check(self._lib.hdt_hash_dag_resolve(self._ctx, pod, len(pod), resolved_pool.data_ptr(), _ptr(prefix_pool), resolved_pool.numel(), rptr, n))
         return ResolvedHashDAG(dag, resolved_pool, prefix_pool)
+
+    # -- multi-GPU host layer behind the C ABI (csrc/hdt_multi.cuh) -------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """hdt_comm_init: NCCL communicator of this context (collective); world == 1 needs no NCCL."""
+        _check(self._lib.hdt_comm_init(self._ctx, C.create_string_buffer(unique_id, 128), rank, world))
+        self.comm_rank, self.comm_world = rank, world
+
+    def replicate(self, tensor, root: int = 0):
+        """hdt_replicate: broadcast a device tensor's bytes from `root` (collective, tracer's stream)."""
+        _check(self._lib.hdt_replicate(self._ctx, tensor.data_ptr(), tensor.numel() * tensor.element_size(), root))
+
+    def broadcast_dirty(self, replica: ReplicaPod, delta: "DagDeltaPod | None", root: int = 0):
+        """hdt_broadcast_dirty: one edit on every rank's replica (pool, page table, resolved / prefix pools); updates replica's root / pool top."""
+        _check(self._lib.hdt_broadcast_dirty(self._ctx, root, C.byref(delta) if delta is not None else None, C.byref(replica)))
+
+    def broadcast_ranges(self, dst_tensor, payload: "np.ndarray | None", ranges: "np.ndarray | None", root: int = 0):
+        """hdt_broadcast_ranges: spans of any replicated uint32 array (the colour tree)."""
+        if payload is None:
+            _check(self._lib.hdt_broadcast_ranges(self._ctx, root, dst_tensor.data_ptr(), dst_tensor.numel(), None, 0, None, 0))
+            return
+        payload = np.ascontiguousarray(payload, dtype=np.uint32)
+        ranges = np.ascontiguousarray(ranges)
+        _check(self._lib.hdt_broadcast_ranges(self._ctx, root, dst_tensor.data_ptr(), dst_tensor.numel(), payload.ctypes.data, payload.size, ranges.ctypes.data, len(ranges)))
 
     def rebuild_color_leaf(self, ops: np.ndarray, old_leaf: "CompressedColorLeaf | None" = None, device=None):
         """Re-encode a colour leaf on the GPU from an op list (color_leaf.OP_DTYPE records = hdt_color_op), see

@@ -37,7 +37,7 @@ enum {
 enum { HDT_DEBUG_NONE = 0, HDT_DEBUG_INDEX, HDT_DEBUG_POSITION, HDT_DEBUG_COLOR_TREE, HDT_DEBUG_COLOR_BITS,
        HDT_DEBUG_MIN_COLOR, HDT_DEBUG_MAX_COLOR, HDT_DEBUG_WEIGHT };
 
-enum { HDT_OK = 0, HDT_ERR_ARG = 1, HDT_ERR_POD_SIZE = 2, HDT_ERR_STATE = 3, HDT_ERR_CAPACITY = 4, HDT_ERR_CUDA = 1000 };
+enum { HDT_OK = 0, HDT_ERR_ARG = 1, HDT_ERR_POD_SIZE = 2, HDT_ERR_STATE = 3, HDT_ERR_CAPACITY = 4, HDT_ERR_NCCL = 5, HDT_ERR_CUDA = 1000 };
 
 /* ---- POD mirrors (device pointers unless the field says _cpu) ------------------------------ */
 typedef struct hdt_array { const void* data; uint64_t size; } hdt_array;                       /* StaticArray<T>,  array.h:8-129  */
@@ -126,8 +126,7 @@ enum {
     HDT_OPT_BEAM_SERIAL = 4,     /* diagnostics, default 0.  1: the per-ray kernels wait for the beam kernel instead of racing it */
     HDT_OPT_EXCHANGE_FUSED = 5,  /* default 0.  1 (needs an exchange, hdt_exchange_*): every shadows pass -- the pass that writes a frame's final
                                     colours -- also stores them into rank 0's frame and its last CTA signals the arrival, so hdt_exchange_frame has
-                                    nothing left to copy.  While set, every shadows pass must be followed by hdt_exchange_frame (a second
-                                    shadows pass before it returns HDT_ERR_STATE). */
+                                    nothing left to copy (a pass repeated before hdt_exchange_frame stores the same frame number again). */
     HDT_OPT_COLORS_RECORDED = 6, /* default 1 (env HDT_COLORS_RECORDED).  For a HDT_DAG_HASH_RESOLVED DAG with a prefix pool, trace_paths also
                                     records, per hit pixel, where the path leaves each ancestor below the colour tree, and trace_colors of the
                                     SAME DAG (same resolved pool, prefix pool and root) reads the voxel's colour index off those records
@@ -214,6 +213,14 @@ int hdt_exchange_create(hdt_ctx* ctx, uint8_t ipc_handle_out[HDT_IPC_HANDLE_BYTE
 int hdt_exchange_open(hdt_ctx* ctx, const uint8_t ipc_handle[HDT_IPC_HANDLE_BYTES]);
 int hdt_exchange_block(hdt_ctx* ctx, void** block_dev_out);
 int hdt_exchange_attach(hdt_ctx* ctx, void* block_dev);
+/* The same exchange with the frame in HOST memory: `host_block` is hdt_exchange_block_bytes() bytes of zero-initialised memory
+ * every rank's process has mapped (POSIX shared memory, an mmap'ed file ...).  EVERY rank, rank 0 included, attaches it; the
+ * library pins and maps it (cudaHostRegister).  hdt_exchange_frame then makes each rank store its own tiles straight into
+ * host memory over its own PCIe link -- the assembled frame never funnels through rank 0's GPU -- and rank 0's stream
+ * waits, as before, until every rank's tiles have landed; after hdt_sync() on rank 0 the host may read frame bytes
+ * [0, W*H*4) of the block.  hdt_exchange_release as before. */
+int hdt_exchange_block_bytes(hdt_ctx* ctx, uint64_t* bytes);
+int hdt_exchange_attach_host(hdt_ctx* ctx, void* host_block, uint64_t bytes);
 int hdt_exchange_frame(hdt_ctx* ctx);
 int hdt_exchange_release(hdt_ctx* ctx);
 
@@ -270,6 +277,63 @@ int hdt_apply_ranges_host(hdt_ctx* ctx, uint32_t* dst_dev, const uint32_t* paylo
  * reference does not clear its pool (hash_table.cpp:60-76); every index read from the pool is bounds-checked. */
 int hdt_hash_dag_resolve(hdt_ctx* ctx, const hdt_hash_dag* dag, size_t dag_size, uint32_t* resolved_pool_dev, uint32_t* prefix_pool_dev_or_null,
                          uint64_t capacity_words, const hdt_range* ranges_host, uint32_t n_ranges);
+
+/* ---- multi-GPU host layer: replicas that follow edits ------------------------------- */
+/* One edit of a HashDAG as the spans it dirtied: what HashTable::upload_to_gpu (hash_table.cpp:120-184) would copy, as
+ * {dst_word, src_word, n_words} records + payload for the pool (physical word indices) and the page table, plus the new
+ * root and pool top (HashDAG::firstNodeIndex, HashTable::poolTop).  All pointers are HOST memory. */
+typedef struct hdt_dag_delta {
+    uint32_t first_node_index, pool_top;
+    const hdt_range* pool_ranges;  uint32_t n_pool_ranges;  const uint32_t* pool_payload;  uint64_t n_pool_payload;
+    const hdt_range* table_ranges; uint32_t n_table_ranges; const uint32_t* table_payload; uint64_t n_table_payload;
+} hdt_dag_delta;
+
+/* The dirty tracker: finds an edit's delta from the hash table's own bookkeeping -- per bucket, its fill count now
+ * (HashTable::cpuData.bucketsSizes) against the count at the previous delta (the reference's lastBucketsSizes,
+ * hash_table.cpp:146-183; the table only appends) -- without comparing arrays: O(#buckets).  `levels` = DAG depth;
+ * bucket_sizes holds at least hdt_tracker_bucket_count() entries in HashDagUtils::get_bucket_global_index order
+ * (hash_table.h:18-35).  hdt_tracker_snapshot records the state of the initial upload; hdt_tracker_delta builds the delta
+ * since the previous snapshot / delta from the host pool and page table (HashTable::cpuData.cpuPool / cpuPageTable) and
+ * advances the snapshot.  The arrays a delta points to belong to the tracker and stay valid until its next call.
+ * A bucket that shrank (undo, garbage collection) is HDT_ERR_STATE: re-upload and take a new snapshot. */
+typedef struct hdt_dirty_tracker hdt_dirty_tracker;
+int hdt_tracker_create(uint32_t levels, hdt_dirty_tracker** out);
+int hdt_tracker_destroy(hdt_dirty_tracker* tracker);
+uint32_t hdt_tracker_bucket_count(const hdt_dirty_tracker* tracker);
+int hdt_tracker_snapshot(hdt_dirty_tracker* tracker, const uint32_t* bucket_sizes, uint32_t n_buckets);
+int hdt_tracker_delta(hdt_dirty_tracker* tracker, const uint32_t* bucket_sizes, uint32_t n_buckets, const uint32_t* cpu_pool, const uint32_t* cpu_page_table,
+                      uint32_t first_node_index, uint32_t pool_top, hdt_dag_delta* out);
+
+/* One process per GPU: an NCCL communicator per context.  libnccl.so.2 is loaded at run time (dlopen; HDT_NCCL_LIB overrides
+ * the name) -- no link-time dependency, and world == 1 never touches it.  Rank 0 obtains the id, the host distributes its
+ * 128 bytes by whatever it has (MPI, sockets, a file), every rank calls hdt_comm_init (collective). */
+#define HDT_COMM_ID_BYTES 128
+int hdt_comm_unique_id(uint8_t id_out[HDT_COMM_ID_BYTES]);
+int hdt_comm_init(hdt_ctx* ctx, const uint8_t id[HDT_COMM_ID_BYTES], uint32_t rank, uint32_t world);
+int hdt_comm_destroy(hdt_ctx* ctx);
+/* Initial replication: broadcast n_bytes of device memory from `root`'s buffer into every rank's buffer,
+ * on the tracer's stream (collective; asynchronous). */
+int hdt_replicate(hdt_ctx* ctx, void* dev_buffer, uint64_t n_bytes, uint32_t root);
+
+/* One GPU's copy of a HashDAG that follows edits.  Device pointers, owned by the caller; resolved_pool / prefix_pool may be
+ * NULL (then only pool and page table are maintained). */
+typedef struct hdt_replica {
+    uint32_t* pool; uint64_t pool_capacity_words;
+    uint32_t* page_table; uint32_t page_table_size;
+    uint32_t first_node_index, pool_top;          /* updated by hdt_broadcast_dirty */
+    uint32_t* resolved_pool; uint32_t* prefix_pool;
+} hdt_replica;
+/* One edit, on every rank (collective): `root` passes the edit's delta, the other ranks NULL.  The delta travels as one
+ * packed buffer (a 32-byte size header first), and every rank applies the page-table and pool spans to ITS replica with
+ * apply_ranges_kernel, re-derives the resolved / prefix pools of the touched pages and updates the replica's root and pool
+ * top -- all enqueued on the tracer's stream, in order with the frames around it (the ranks other than root synchronise
+ * their stream once, to learn the sizes).  With world == 1 (no communicator needed) it simply applies the delta.
+ * Replaces, for N GPUs, HashTable::upload_to_gpu (hash_table.cpp:120-184; Engine::edit, engine.h:77-103). */
+int hdt_broadcast_dirty(hdt_ctx* ctx, uint32_t root, const hdt_dag_delta* delta_or_null, hdt_replica* replica);
+/* The building block, for any replicated array of 32-bit words (the HashDAGColors tree, hash_dag_colors.h:102-120): `root`
+ * passes spans + payload (HOST; the others NULL / 0), every rank applies them to its dst_dev.  Collective, tracer's stream. */
+int hdt_broadcast_ranges(hdt_ctx* ctx, uint32_t root, uint32_t* dst_dev, uint64_t dst_capacity_words, const uint32_t* payload_host, uint64_t n_payload_words,
+                         const hdt_range* ranges_host, uint32_t n_ranges);
 
 /* Kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t hdt_launch_count(const hdt_ctx* ctx);

@@ -20,7 +20,7 @@ mkdir -p ab_libs
 if [ "$1" = "build" ]; then
     for v in "${VARIANTS[@]}"; do
         n=${v%%:*}; f=${v#*:}
-        nvcc $FLAGS $f -o ab_libs/lib_$n.so hashdag_b200/csrc/hdt_tracer.cu &
+        nvcc $FLAGS $f -o ab_libs/lib_$n.so hashdag_b200/csrc/hdt_tracer.cu -ldl &
     done
     wait
     ls -la ab_libs

@@ -57,6 +57,9 @@ def main(recipe="d13"):
     vpool, vtable, vsizes = rt.hash_views()          # the reference's live host arrays + per-bucket fill counts
     assert vsizes.size == layout.n_buckets and vtable.size == layout.n_pages
     last_sizes = vsizes.copy()
+    tracker = tracer.DirtyTracker(scene.levels)      # the product's tracker (C++, hdt_tracker_*); the numpy twin below checks it
+    assert tracker.n_buckets == layout.n_buckets
+    tracker.snapshot(vsizes)
     for k, (centre, radius, adding) in enumerate(plan):
         rt.edit_sphere(centre, radius, adding)
         npool, ntable, nfirst, ntop = rt.hash_dag()
@@ -66,13 +69,17 @@ def main(recipe="d13"):
         # the product path: spans from the hash table's own bookkeeping, no array comparison (edits.delta_from_bucket_sizes)
         delta = edits.add_color_delta(edits.delta_from_bucket_sizes(layout, last_sizes, vsizes, vpool, vtable, nfirst, ntop), nodes, nnodes, leaves_host, nleaves)
         last_sizes = vsizes.copy()
+        pod = tracker.delta_pod(vsizes, vpool, vtable, nfirst, ntop)
+        for a, b in zip(tracer.DirtyTracker.arrays(pod), (delta.pool_ranges, delta.pool_payload, delta.table_ranges, delta.table_payload)):
+            assert np.array_equal(a, b), "hdt_tracker_delta differs from edits.delta_from_bucket_sizes"
+        assert (pod.first_node_index, pod.pool_top) == (nfirst, ntop)
         assert delta.pool_payload.size <= 2 * full.pool_payload.size + 64 * max(1, len(delta.pool_ranges))
         # host mirror of the device apply: the delta alone reproduces the new arrays
         hp = np.zeros(max(pool.size, ntop * 512), np.uint32); hp[: pool.size] = pool
         edits.apply_spans_host(hp, delta.pool_ranges, delta.pool_payload)
         ht = table.copy(); edits.apply_spans_host(ht, delta.table_ranges, delta.table_payload)
         assert np.array_equal(hp[: ntop * 512], npool) and np.array_equal(ht, ntable)
-        rep.apply(delta)
+        rep.apply(delta, pod=pod)                    # pool / page table straight from the tracker's arrays (hdt_broadcast_dirty)
         full = npool.nbytes + ntable.nbytes + nnodes.nbytes
         changed = int((nfirst != first) or len(delta.pool_ranges) > 0)
         pool, table, first, top, nodes, leaves_host = npool, ntable, nfirst, ntop, nnodes, nleaves
