@@ -193,27 +193,6 @@ def product_implementation(args, world):
     }
 
 
-class stdout_to_stderr:
-    """The reference prints its progress with printf (hash_dag_factory.cpp, memory.cpp); bench.py's stdout carries ONE JSON
-    line, so while reference code runs, file descriptor 1 points at stderr (C stdio flushed on both sides)."""
-
-    def __enter__(self):
-        import ctypes
-        self.libc = ctypes.CDLL(None)
-        sys.stdout.flush()
-        self.libc.fflush(None)
-        self.saved = os.dup(1)
-        os.dup2(2, 1)
-        return self
-
-    def __exit__(self, *exc):
-        sys.stdout.flush()
-        self.libc.fflush(None)
-        os.dup2(self.saved, 1)
-        os.close(self.saved)
-        return False
-
-
 def time_reference_kernels(rt, poses, info, step_ids, warmup_ids, dk, ck):
     """The reference's three synchronous calls per frame (dag_tracer.cu:116-219), timed by its own cudaEvents (:130-138)."""
     for i in warmup_ids:
@@ -235,8 +214,6 @@ def run_reference_cuda(args):
     W, H = resolution(args, 1)
     scene, poses = workloads.build_workload(args.levels, args.footprint_log2, args.poses)
     info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
-    guard = stdout_to_stderr()
-    guard.__enter__()
     rt = ref.RefTracer(args.levels, W, H)
     rt.load_scene(scene)
     hashed = args.dag == "hash"
@@ -257,7 +234,6 @@ def run_reference_cuda(args):
             rays += W * H + hits[i % len(poses)]
     total_ms = tp + tc + ts
     rt.close()
-    guard.__exit__()
     print(json.dumps({
         "impl": "reference-cuda", "metric": METRIC, "value": rays / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "dtype": "f32+f64+u32", "data": "synthetic",
@@ -502,9 +478,15 @@ def run_ours(args):
             dist.broadcast_object_list(box, src=0)
             if rank != 0:
                 shm = shared_memory.SharedMemory(name=box[0])
+                try:   # only the creator unlinks: keep Python's resource tracker from trying (and warning) in the other ranks
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(shm._name, "shared_memory")
+                except Exception:
+                    pass
             view = np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)
             t_.exchange_attach_host(view.ctypes.data, nbytes)
             host_lanes.append(t_); host_shm.append(shm); host_views.append(view)
+        del view
         dist.barrier()
         for i in range(2):          # warm-up: first touch of the mapped pages, one frame per lane
             host_lanes[i].enqueue_frame(params[i], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
@@ -641,7 +623,12 @@ def run_ours(args):
             host_lanes[0].exchange_frame()
             host_lanes[0].sync()
             if rank == 0:
-                got = host_views[0][: W * H * 4].view(np.uint32).reshape(H, W).copy()
+                from hashdag_b200 import partition
+                T = 1 << tile_log2
+                mt = partition.max_tiles_per_rank(world, W, H, tile_log2)
+                tiles = host_views[0][: world * mt * T * T * 4].view(np.uint32).reshape(world, mt, T, T)
+                got = partition.assemble([tiles[r] for r in range(world)], W, H, tile_log2)    # the host frame is in tile layout
+                del tiles
                 host_lanes[0].exchange_release()
                 whole.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, None)
                 host_mismatch += int((whole.read_colors() != got).sum())
@@ -649,10 +636,14 @@ def run_ours(args):
             whole.close()
         barrier()
         for t_ in host_lanes:
-            t_.close()
+            t_.close()          # unregisters the pinned mapping
         del host_views[:]
+        got = None
         for shm in host_shm:
-            shm.close()
+            try:
+                shm.close()
+            except BufferError:  # a view is still alive somewhere: the mapping goes with the process
+                pass
             if rank == 0:
                 shm.unlink()
 
@@ -681,7 +672,8 @@ def run_ours(args):
         out["parity_check_mismatched_pixels_vs_whole_frame_on_rank0"] = exchange_mismatch
     if host_mismatch is not None:
         out["parity_check_mismatched_pixels_host_frame_vs_whole_frame_on_rank0"] = host_mismatch
-        out["e2e"]["path"] = "every rank stores its tiles into pinned host memory shared by the ranks (hdt_exchange_attach_host), two frames in flight"
+        out["e2e"]["path"] = ("every rank copies its compact tile buffer into its slice of pinned host memory shared by the ranks over its own PCIe link "
+                              "(hdt_exchange_attach_host: one copy-engine transfer per rank and frame, tile layout), two frames in flight")
     if single_ms:
         single_value = rays / (single_ms * 1e-3 * args.steps) / 1e6
         out["single_gpu_same_workload"] = {"ms_per_step": single_ms, "value": single_value, "unit": UNIT, "frames_in_flight": 3,
@@ -763,16 +755,15 @@ def run_ours(args):
             for i in sample_ids[:2]:
                 tr.resolve_frame(poses[i], info, dag, colors, 1.0, 0.0, True, host_frame)
                 ours_img[i] = host_frame.numpy().view(np.uint32).reshape(H, W).copy()
-            with stdout_to_stderr():
-                rt = ref.RefTracer(args.levels, W, H)
-                rt.load_scene(scene)
-                dk, ck = (1, 3) if hashed else (0, 1)
-                ref_ms = time_reference_kernels(rt, poses, info, step_ids, warm_ids, dk, ck)
-                ref_bad = 0
-                for i in sample_ids[:2]:
-                    rt.resolve_paths(dk, poses[i], info); rt.resolve_colors(dk, ck); rt.resolve_shadows(dk, poses[i], info, 1.0, 0.0)
-                    ref_bad += int((rt.read_colors() != ours_img[i]).sum())
-                rt.close()
+            rt = ref.RefTracer(args.levels, W, H)       # (the reference prints its progress: descriptor 1 is stderr, see main())
+            rt.load_scene(scene)
+            dk, ck = (1, 3) if hashed else (0, 1)
+            ref_ms = time_reference_kernels(rt, poses, info, step_ids, warm_ids, dk, ck)
+            ref_bad = 0
+            for i in sample_ids[:2]:
+                rt.resolve_paths(dk, poses[i], info); rt.resolve_colors(dk, ck); rt.resolve_shadows(dk, poses[i], info, 1.0, 0.0)
+                ref_bad += int((rt.read_colors() != ours_img[i]).sum())
+            rt.close()
             ref_total = sum(ref_ms.values())
             out["ref_cuda"] = {"what": "oracle/_ref: the UNMODIFIED reference kernels (tracer.cu:145-697 via dag_tracer.cu:116-219) compiled for sm_100a, same GPU, "
                                        "DAG and the same K poses, after the timed region; kernel times from the reference's own cudaEvents, three synchronous calls per frame",
@@ -843,16 +834,20 @@ def replicas_from_tensors(tracer, t, meta, hashed):
 
 def main():
     args = parse_args()
+    # ONE JSON line on stdout.  Native libraries write to file descriptor 1 behind Python's back (NCCL's version banner, the
+    # reference's progress messages and its "No leaks!" from a static destructor at exit), so descriptor 1 is pointed at
+    # stderr for the whole run and Python's sys.stdout keeps the real stdout for the one line this script prints.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference_cpu(args)
     elif args.impl == "reference-cuda":
         run_reference_cuda(args)
     else:
         run_ours(args)
-    # ONE JSON line on stdout: whatever native libraries print while the process winds down (the reference's memory tracker
-    # reports "No leaks!" from a static destructor) goes to stderr
     sys.stdout.flush()
-    os.dup2(2, 1)
 
 
 if __name__ == "__main__":

@@ -64,6 +64,10 @@ static_assert(kBlockW % 8 == 0 && kBlockH % 4 == 0 && kBlockW <= 32 && kBlockH <
 __device__ __forceinline__ bool warp_pixel(const PixelMap& m, u32 block, u32 warp, u32 lane, u32& x, u32& y)
 {
     const u32 T = 1u << m.tileLog2, blocksX = T / kBlockW, blocksPerTile = blocksX * (T / kBlockH);
+    // Units are launched in storage order, one CTA each, placed by the hardware scheduler.  Measured and rejected on B200
+    // (profiles/r2_ab.md): spreading the launch order over the screen (slot * k mod nOwned, to keep the horizon's expensive
+    // tiles out of the last wave): +10 % on both traversal kernels -- the CTAs resident together lose the cache lines they
+    // share; resident CTAs fetching units from per-SM runs of neighbouring tiles (SM-affine persistent kernel): +27 %.
     const u32 slot = block / blocksPerTile, b = block % blocksPerTile;
     const u32 t = m.rank + slot * m.world;
     const u32 tx = t % m.tilesX, ty = t / m.tilesX;
@@ -1263,7 +1267,13 @@ int hdt_apply_ranges(hdt_ctx* c, uint32_t* dst_dev, const uint32_t* payload_dev,
 
 // ---- framebuffer exchange over peer memory (hdt_exchange.cuh) ---------------------------------------
 namespace {
-size_t exchange_frame_bytes(const hdt_ctx* c) { return (size_t(c->map.width) * c->map.height * 4 + 255) & ~size_t(255); }
+// frame part of an exchange block: row-major W x H (device block), or -- host block -- every rank's compact tile buffer
+// (maxTilesPerRank tiles) back to back
+size_t exchange_frame_bytes(const hdt_ctx* c)
+{
+    if (c->xHostBlock) return (size_t(c->map.world) * c->maxTilesPerRank * (size_t(4) << (2 * c->map.tileLog2)) + 255) & ~size_t(255);
+    return (size_t(c->map.width) * c->map.height * 4 + 255) & ~size_t(255);
+}
 ExchangeCounters* exchange_counters(const hdt_ctx* c) { return reinterpret_cast<ExchangeCounters*>(reinterpret_cast<char*>(c->xBlock) + exchange_frame_bytes(c)); }
 int exchange_common(hdt_ctx* c)
 {
@@ -1339,7 +1349,7 @@ int hdt_exchange_attach(hdt_ctx* c, void* block_dev)
 int hdt_exchange_block_bytes(hdt_ctx* c, uint64_t* bytes)
 {
     if (!c || !bytes) return fail(HDT_ERR_ARG, "null argument");
-    *bytes = exchange_frame_bytes(c) + sizeof(ExchangeCounters);
+    *bytes = ((size_t(c->map.world) * c->maxTilesPerRank * (size_t(4) << (2 * c->map.tileLog2)) + 255) & ~size_t(255)) + sizeof(ExchangeCounters);
     return HDT_OK;
 }
 
@@ -1347,7 +1357,9 @@ int hdt_exchange_attach_host(hdt_ctx* c, void* host_block, uint64_t bytes)
 {
     if (!c || !host_block) return fail(HDT_ERR_ARG, "null argument");
     if (c->xBlock) return fail(HDT_ERR_STATE, "hdt_exchange_attach_host: the context already has an exchange");
-    if (bytes < exchange_frame_bytes(c) + sizeof(ExchangeCounters)) return fail(HDT_ERR_CAPACITY, "hdt_exchange_attach_host: block smaller than hdt_exchange_block_bytes");
+    uint64_t need = 0;
+    hdt_exchange_block_bytes(c, &need);
+    if (bytes < need) return fail(HDT_ERR_CAPACITY, "hdt_exchange_attach_host: block smaller than hdt_exchange_block_bytes");
     HDT_CUDA(cudaSetDevice(c->device));
     // pin + map the caller's (shared) memory; a second context of this process finds it registered already
     cudaError_t e = cudaHostRegister(host_block, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
@@ -1356,8 +1368,9 @@ int hdt_exchange_attach_host(hdt_ctx* c, void* host_block, uint64_t bytes)
     else c->xHostRegistered = true;
     void* dev = nullptr;
     HDT_CUDA(cudaHostGetDevicePointer(&dev, host_block, 0));
-    c->xBlock = static_cast<u32*>(dev);
+    c->xBlock = static_cast<u32*>(dev);     // device alias: the counters behind the frame are polled / written by kernels
     c->xHostBlock = host_block;
+    if (c->xFused) return fail(HDT_ERR_STATE, "hdt_exchange_attach_host: not with HDT_OPT_EXCHANGE_FUSED");
     return exchange_common(c);
 }
 
@@ -1370,10 +1383,29 @@ int hdt_exchange_frame(hdt_ctx* c)
     ExchangeCounters* k = exchange_counters(c);
     u32* timedOutDev = c->xTimedOutDev;
     const u32 T = 1u << c->map.tileLog2;
-    const bool fused = c->xFusedSeq == seq && c->grid_blocks() > 0;   // the last shadow pass already stored (and signalled) this frame
-    const u32 grid = fused ? 0 : c->nOwnedTiles * (T / 16);
     const bool root = c->map.rank == 0;
     u32* abortDev = c->xCtasDone + 1;
+    if (c->xHostBlock) {
+        // host block: this rank's compact tile buffer goes to its slice of the shared host frame in ONE copy-engine transfer
+        // over the rank's own PCIe link; the arrival word follows in stream order
+        const size_t tileBytes = size_t(4) << (2 * c->map.tileLog2), slice = size_t(c->maxTilesPerRank) * tileBytes;
+        if (!root) {
+            exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, 1, seq - 1, c->xWaitCycles, timedOutDev, abortDev);
+            HDT_LAUNCHED("exchange_wait_kernel");
+        }
+        if (c->nOwnedTiles)
+            HDT_CUDA(cudaMemcpyAsync(static_cast<char*>(c->xHostBlock) + size_t(c->map.rank) * slice, c->colors, size_t(c->nOwnedTiles) * tileBytes, cudaMemcpyDeviceToHost, c->stream));
+        if (!root) {
+            exchange_signal_kernel<<<1, 1, 0, c->stream>>>(&k->arrived[c->map.rank], seq, abortDev);
+            HDT_LAUNCHED("exchange_signal_kernel");
+        } else if (c->map.world > 1) {
+            exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->arrived[1], c->map.world - 1, seq, c->xWaitCycles, timedOutDev, abortDev);
+            HDT_LAUNCHED("exchange_wait_kernel");
+        }
+        return HDT_OK;
+    }
+    const bool fused = c->xFusedSeq == seq && c->grid_blocks() > 0;   // the last shadow pass already stored (and signalled) this frame
+    const u32 grid = fused ? 0 : c->nOwnedTiles * (T / 16);
     if (!root && !fused) {   // the root must have consumed the previous frame of this lane before it is overwritten
         exchange_wait_kernel<<<1, 1, 0, c->stream>>>(&k->credit, 1, seq - 1, c->xWaitCycles, timedOutDev, abortDev);
         HDT_LAUNCHED("exchange_wait_kernel");

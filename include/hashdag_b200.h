@@ -215,10 +215,13 @@ int hdt_exchange_block(hdt_ctx* ctx, void** block_dev_out);
 int hdt_exchange_attach(hdt_ctx* ctx, void* block_dev);
 /* The same exchange with the frame in HOST memory: `host_block` is hdt_exchange_block_bytes() bytes of zero-initialised memory
  * every rank's process has mapped (POSIX shared memory, an mmap'ed file ...).  EVERY rank, rank 0 included, attaches it; the
- * library pins and maps it (cudaHostRegister).  hdt_exchange_frame then makes each rank store its own tiles straight into
- * host memory over its own PCIe link -- the assembled frame never funnels through rank 0's GPU -- and rank 0's stream
- * waits, as before, until every rank's tiles have landed; after hdt_sync() on rank 0 the host may read frame bytes
- * [0, W*H*4) of the block.  hdt_exchange_release as before. */
+ * library pins and maps it (cudaHostRegister).  hdt_exchange_frame then copies each rank's compact tile buffer into its
+ * slice of the block in ONE copy-engine transfer over the rank's own PCIe link -- the frame never funnels through rank
+ * 0's GPU or its single link -- followed by the rank's arrival word; rank 0's stream waits, as before, until every rank
+ * has arrived: after hdt_sync() on rank 0 the host owns the frame.  Layout of the block's frame part: rank r's slice
+ * starts at byte r * max_tiles_per_rank * tile_bytes and holds its owned tiles back to back, each tile row-major --
+ * tile t of the screen (row-major tile numbering) is slot t / world of rank t % world, the layout of
+ * hdt_partition_buffers.  hdt_exchange_release as before.  Not combinable with HDT_OPT_EXCHANGE_FUSED. */
 int hdt_exchange_block_bytes(hdt_ctx* ctx, uint64_t* bytes);
 int hdt_exchange_attach_host(hdt_ctx* ctx, void* host_block, uint64_t bytes);
 int hdt_exchange_frame(hdt_ctx* ctx);

@@ -108,14 +108,20 @@ def main():
         name = None
         if rank == 0:
             shm = shared_memory.SharedMemory(create=True, size=nbytes)
-            shm.buf[:nbytes] = bytes(nbytes) if nbytes < (1 << 20) else np.zeros(nbytes, np.uint8).tobytes()
             name = shm.name
         name = share(name)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name)
+            try:   # only the creator unlinks
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         block = np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)
         t.exchange_attach_host(block.ctypes.data, nbytes)
-        frame_host = block[: W * H * 4].view(np.uint32).reshape(H, W)
+        from hashdag_b200 import partition
+        mt, T = partition.max_tiles_per_rank(world, W, H, 6), 64
+        frame_host = block[: world * mt * T * T * 4].view(np.uint32).reshape(world, mt, T, T)     # tile layout: rank-major compact tile buffers
         dist.barrier()
 
     per_edit, bad_total = [], 0
@@ -156,7 +162,7 @@ def main():
         t.sync()
         h3 = time.perf_counter()
         if rank == 0:
-            img = frame_host.copy() if world > 1 else t.read_colors()
+            img = partition.assemble([frame_host[r] for r in range(world)], W, H, 6) if world > 1 else t.read_colors()
             if world > 1:
                 t.exchange_release()
             ra = rt.resolve_paths(1, pose, info)
@@ -184,7 +190,10 @@ def main():
         rt.close()
     if shm is not None:
         del frame_host, block
-        shm.close()
+        try:
+            shm.close()
+        except BufferError:
+            pass
         if rank == 0:
             shm.unlink()
     if world > 1:
