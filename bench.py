@@ -464,10 +464,10 @@ def run_ours(args):
     host_frames = [host_frame] + [torch.empty(W * H, dtype=torch.int32).pin_memory() for _ in lanes[1:]] if rank == 0 else None
     host_lanes, host_shm, host_views = [], [], []
     if world > 1 and args.e2e_exchange == "host" and not os.environ.get("HDT_BENCH_NO_GATHER"):
-        # N > 1: two more contexts per rank whose exchange block is pinned HOST memory shared by all ranks (POSIX shared memory):
+        # N > 1: three more contexts per rank whose exchange block is pinned HOST memory shared by all ranks (POSIX shared memory):
         # every rank pushes its own tiles over its own PCIe link, nothing funnels through rank 0's GPU
         from multiprocessing import shared_memory
-        for _ in range(2):
+        for _ in range(3):
             t_ = tracer.DAGTracer(True, W, H, args.levels, device=local_rank)
             t_.set_partition(rank, world, tile_log2)
             nbytes = t_.exchange_block_bytes()
@@ -488,7 +488,7 @@ def run_ours(args):
             host_lanes.append(t_); host_shm.append(shm); host_views.append(view)
         del view
         dist.barrier()
-        for i in range(2):          # warm-up: first touch of the mapped pages, one frame per lane
+        for i in range(len(host_lanes)):          # warm-up: first touch of the mapped pages, one frame per lane
             host_lanes[i].enqueue_frame(params[i], dag_pod, dag.kind, col_pod, colors.kind, 1.0, 0.0, True, None)
             host_lanes[i].exchange_frame()
         for t_ in host_lanes:
@@ -503,8 +503,8 @@ def run_ours(args):
         if host_lanes:
             # frame i: kernels -> tiles stored into the shared host frame of lane k (+ arrival flags); a lane is synchronised -- on
             # rank 0 that means the whole frame is in host memory -- and released before it is given the next frame
-            k = i % 2
-            if i >= 2:
+            k = i % len(host_lanes)
+            if i >= len(host_lanes):
                 host_lanes[k].sync()
                 if rank == 0:
                     host_lanes[k].exchange_release()
@@ -673,7 +673,7 @@ def run_ours(args):
     if host_mismatch is not None:
         out["parity_check_mismatched_pixels_host_frame_vs_whole_frame_on_rank0"] = host_mismatch
         out["e2e"]["path"] = ("every rank copies its compact tile buffer into its slice of pinned host memory shared by the ranks over its own PCIe link "
-                              "(hdt_exchange_attach_host: one copy-engine transfer per rank and frame, tile layout), two frames in flight")
+                              "(hdt_exchange_attach_host: one copy-engine transfer per rank and frame, tile layout), three frames in flight")
     if single_ms:
         single_value = rays / (single_ms * 1e-3 * args.steps) / 1e6
         out["single_gpu_same_workload"] = {"ms_per_step": single_ms, "value": single_value, "unit": UNIT, "frames_in_flight": 3,
