@@ -711,16 +711,24 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         dominant = max(gpu_ms_pass, key=lambda k: gpu_ms_pass[k])
-        traffic = None
+        traffic, limiter = None, None
         ncu_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
         if os.path.exists(ncu_path):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the pass' kernels, same config
             try:
-                traffic = json.load(open(ncu_path)).get("dram_bytes_per_pass", {}).get(dominant)
+                ncu = json.load(open(ncu_path))
+                traffic = ncu.get("dram_bytes_per_pass", {}).get(dominant)
+                k = next((v for n, v in ncu.get("kernels", {}).items() if n.startswith(f"trace_{dominant}")), None)
+                if k:   # what the counters say bounds the kernel (the HBM figure above is the SURVEY §8d algorithmic-bytes roofline)
+                    limiter = {"what": "instruction issue" if k.get("issue_active_pct", 0) > 60 and k.get("dram_pct_of_peak", 100) < 40 else "memory latency",
+                               "issue_slots_busy_pct": k.get("issue_active_pct"), "threads_per_warp_instruction": k.get("threads_per_warp_inst"),
+                               "dram_pct_of_peak": k.get("dram_pct_of_peak"), "l1_hit_pct": k.get("l1_hit_pct"), "l2_hit_pct": k.get("l2_hit_pct"),
+                               "warp_instructions_per_launch": k.get("warp_inst_executed"), "source": "profiles/ncu_summary.json (ncu --set full of the shipped kernels, round 2)"}
             except Exception:
                 traffic = None
         ach = {k: (bytes_pass[k] / (gpu_ms_pass[k] * 1e-3) / 1e9 if gpu_ms_pass[k] > 0 else 0.0) for k in bytes_pass}
         out["roofline"] = {"bound": "hbm", "kernel": f"{dominant} pass = setup_{dominant}_kernel + beam_{dominant}_kernel + trace_{dominant}_kernel" if dominant != "colors" else "trace_colors_kernel", "achieved": ach[dominant], "peak": peak, "unit": "GB/s",
                            "frac": ach[dominant] / peak, "traffic": traffic, "peak_source": peak_src,
+                           "limited_by": limiter,
                            "algorithmic_bytes_per_launch": bytes_pass[dominant] / len(sample_ids),
                            "avg_launch_ms": gpu_ms_pass[dominant] / len(sample_ids),
                            "per_pass": {k: {"ms": gpu_ms_pass[k] / len(sample_ids), "algorithmic_GBps": ach[k],

@@ -24,12 +24,16 @@ M = {
     "stall_not_selected": "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "stall_math_pipe_throttle": "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "stall_wait": "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "issue_active_per_cycle": "smsp__issue_active.avg.per_cycle_active",
+    "local_load_sectors": "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "local_store_sectors": "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+    "local_load_hit_pct": "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct",
+    "dram_pct_of_peak": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
 }
 scale = {"Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6, "Gbyte": 1e3, "us": 1.0, "ms": 1e3, "ns": 1e-3, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3}
 acc = collections.defaultdict(lambda: collections.defaultdict(list))
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "").replace("hdt::", "")
+    short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "").replace("hdt::", "").replace("HashDagResolvedDevT<(bool)1>", "HashDagPrefixDev").replace("HashDagResolvedDevT<(bool)0>", "HashDagResolvedDev")
     for k, m in M.items():
         if m not in ix or r[ix[m]] in ("", "n/a"):
             continue
@@ -43,7 +47,7 @@ per_pass = {}
 for p in ("paths", "shadows", "colors"):
     tot = 0.0
     for n, d in kernels.items():
-        if p in n and ("HashDagDev" in n or "HashDagResolvedDev" in n) or (p in n and "setup_" in n):
+        if p in n and ("HashDagDev" in n or "HashDagResolvedDev" in n or "HashDagPrefixDev" in n or "recorded" in n) or (p in n and "setup_" in n):
             tot += (d.get("dram_read_MB", 0) + d.get("dram_write_MB", 0)) * 1e6
     per_pass[p] = tot
 json.dump({"source": rep + " (ncu --set full --clock-control none; per-launch averages; cold caches, kernels serialised)",
