@@ -497,6 +497,9 @@ struct hdt_ctx {
     cudaStream_t side = nullptr;        // beam kernels run here, concurrently with the per-ray kernels
     cudaEvent_t fork[2] = {}, setupDone[2] = {}, join[2] = {}, traceDone[2] = {};   // per pass; traceDone[0] also gates the prefetch
     bool useBeams = true;
+    bool l2Persist = true;              // HDT_OPT_L2_PERSIST: page table of a plain HashDAG pinned in L2 (access policy window)
+    const void* l2Window = nullptr;     // what the streams' access policy window currently covers
+    size_t l2WindowBytes = 0;
     bool beamPrefetch = false;
     bool beamSerial = false;            // diagnostics: per-ray kernels wait for the beam kernel
     u32 beamMaxVisits = 32;
@@ -587,6 +590,7 @@ int configure(hdt_ctx* c, u32 rank, u32 world, u32 tileLog2)
 
 struct DagArg {
     int kind; BasicDagDev basic; HashDagDev hash; HashDagResolvedDev resolved;
+    u32 pageTableSize = 0;   // HashDAG kinds: entries of the page table
     // a resolved HashDAG with a prefix pool, seen through the accessor that reads leaf masks from it (per-ray traversal kernels)
 #ifdef HDT_NO_PREFIX_LEAF_MASK   // A/B switch: traverse through the plain resolved accessor even when a prefix pool is there
     bool has_prefix() const { return false; }
@@ -613,6 +617,7 @@ int parse_dag(int kind, const void* pod, size_t size, DagArg& out)
         if (!d.pool || !d.page_table) return fail(HDT_ERR_ARG, "HashDAG: null pool / page table");
         if (u64(d.pool_top) * kPageWords > (u64(1) << 32)) return fail(HDT_ERR_ARG, "HashDAG: pool beyond 2^32 words");
         out.hash.pool = d.pool; out.hash.pageTable = d.page_table; out.hash.firstNodeIndex = d.first_node_index;
+        out.pageTableSize = d.page_table_size;
         return HDT_OK;
     }
     if (kind == HDT_DAG_HASH_RESOLVED) {
@@ -709,6 +714,36 @@ ShadowParams make_shadow(float bias, float fog)
 // Launch tags run through 0 .. 2^30-2; the state buffers are initialised with 2^30-1.
 u32 next_beam_tag(hdt_ctx* c) { return c->beamTag = (c->beamTag + 1) % 0x3FFFFFFFu; }
 
+// A plain HashDAG (HDT_DAG_HASH, what a drop-in caller passes) is traced through its page table: one 4-byte entry per node
+// visited, scattered over 16 MiB at depth 17 (hash_table.h:156-173).  The table is declared persisting in L2 for the tracer's
+// streams (B200: 126 MB of L2), so the streaming node and leaf loads of a frame cannot evict it; the window is (re)set only
+// when the table's address or size changes.  The resolved pool does not read the page table while traversing.
+int pin_page_table(hdt_ctx* c, const DagArg& d, uint32_t pageTableEntries)
+{
+    const void* base = (d.kind == HDT_DAG_HASH && c->l2Persist) ? static_cast<const void*>(d.hash.pageTable) : nullptr;
+    const size_t bytes = base ? size_t(pageTableEntries) * 4 : 0;
+    if (base == c->l2Window && bytes == c->l2WindowBytes) return HDT_OK;
+    if (base && !c->l2WindowBytes) {   // first use: set aside L2 for persisting lines (device-wide limit; errors here are not fatal)
+        int maxPersist = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+        if (maxPersist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(size_t(maxPersist), size_t(64) << 20));
+        cudaGetLastError();
+    }
+    cudaStreamAttrValue attr{};
+    int maxWindow = 0;
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr.accessPolicyWindow.num_bytes = std::min(bytes, size_t(maxWindow > 0 ? maxWindow : 0));
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = base ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (!base) attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    for (cudaStream_t st : { c->stream, c->side })
+        if (st && cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) { cudaGetLastError(); break; }
+    c->l2Window = base; c->l2WindowBytes = bytes;
+    return HDT_OK;
+}
+
 // Every launch helper returns HDT_OK or the code of the first failing CUDA call (named in hdt_last_error()).
 #define HDT_LAUNCHED(what)                                       \
     do {                                                         \
@@ -722,6 +757,7 @@ int launch_paths(hdt_ctx* c, const DagArg& d, const CameraParams& cam)
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     c->ancValid = false;
     if (!grid.x) return HDT_OK;
+    if (int rc = pin_page_table(c, d, d.pageTableSize)) return rc;
     // Ray setup and beams on the side stream.  Normally they are ordered after everything enqueued on the
     // main stream so far.  With HDT_OPT_BEAM_PREFETCH the caller promises that the DAG is not modified by
     // work queued on the tracer's stream, and they only wait for the previous paths kernel (the last
@@ -775,6 +811,7 @@ int launch_colors(hdt_ctx* c, const DagArg& d, const ColorsDev& col, const Color
 {
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     if (!grid.x) return HDT_OK;
+    if (int rc = pin_page_table(c, d, d.pageTableSize)) return rc;
     if (colors_recorded_ok(c, d, col, prm))
     {
         trace_colors_recorded_kernel<<<grid, block, 0, c->stream>>>(d.resolved.prefix, col, c->levels, prm, c->map, c->paths, c->anc[0], c->anc[1], c->colors);
@@ -796,6 +833,7 @@ int prepare_shadows(hdt_ctx* c, const DagArg& d, const CameraParams& cam, const 
     const dim3 grid(c->grid_blocks()), block(kBlockThreads);
     if (!grid.x) return HDT_OK;
     prep.valid = true;
+    if (int rc = pin_page_table(c, d, d.pageTableSize)) return rc;
     HDT_CUDA(cudaEventRecord(c->fork[1], c->stream));
     HDT_CUDA(cudaStreamWaitEvent(c->side, c->fork[1], 0));
     setup_shadows_kernel<<<grid, block, 0, c->side>>>(cam, sp, c->map, c->paths, c->ray_planes(1), c->seeds[1]);
@@ -900,6 +938,7 @@ int hdt_create(uint32_t width, uint32_t height, uint32_t levels, int device, hdt
     if (const char* env = getenv("HDT_BEAMS")) c->useBeams = atoi(env) != 0;
     if (const char* env = getenv("HDT_BEAM_PREFETCH")) c->beamPrefetch = atoi(env) != 0;
     if (const char* env = getenv("HDT_COLORS_RECORDED")) c->useRecorded = atoi(env) != 0;
+    if (const char* env = getenv("HDT_L2_PERSIST")) c->l2Persist = atoi(env) != 0;
     if (const char* env = getenv("HDT_BEAM_MAX_VISITS")) c->beamMaxVisits = u32(atoi(env) > 0 ? atoi(env) : 1);
     cudaError_t e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking);
     c->stream = c->ownStream;
@@ -973,6 +1012,7 @@ int hdt_set_option(hdt_ctx* c, int option, int value)
     if (option == HDT_OPT_BEAM_PREFETCH) { c->beamPrefetch = value != 0; return HDT_OK; }
     if (option == HDT_OPT_BEAM_SERIAL) { c->beamSerial = value != 0; return HDT_OK; }
     if (option == HDT_OPT_EXCHANGE_FUSED) { c->xFused = value != 0; return HDT_OK; }
+    if (option == HDT_OPT_L2_PERSIST) { c->l2Persist = value != 0; return HDT_OK; }
     if (option == HDT_OPT_COLORS_RECORDED) { c->useRecorded = value != 0; c->ancValid = false; return HDT_OK; }
     if (option == HDT_OPT_EXCHANGE_TIMEOUT_MS) {
         if (value < 0) return fail(HDT_ERR_ARG, "exchange timeout must be >= 0 ms (0 = wait for ever)");

@@ -26,7 +26,7 @@ LIB_PATH = os.environ.get("HDT_LIB", os.path.join(_HERE, "libhashdag_b200.so")) 
 DAG_BASIC, DAG_HASH, DAG_HASH_RESOLVED = 0, 1, 2
 COLORS_UNCOMPRESSED, COLORS_COMPRESSED, COLORS_ERRORS, COLORS_HASH = 0, 1, 2, 3
 UNIQUE_OFFSET = 0xFFFFFFFFFFFFFFFF
-OPT_BEAMS, OPT_BEAM_MAX_VISITS, OPT_BEAM_PREFETCH, OPT_BEAM_SERIAL, OPT_EXCHANGE_FUSED, OPT_COLORS_RECORDED, OPT_EXCHANGE_TIMEOUT_MS = 1, 2, 3, 4, 5, 6, 7
+OPT_BEAMS, OPT_BEAM_MAX_VISITS, OPT_BEAM_PREFETCH, OPT_BEAM_SERIAL, OPT_EXCHANGE_FUSED, OPT_COLORS_RECORDED, OPT_EXCHANGE_TIMEOUT_MS, OPT_L2_PERSIST = 1, 2, 3, 4, 5, 6, 7, 8
 
 # EDebugColors, tracer.h:7-17
 DEBUG_NONE, DEBUG_INDEX, DEBUG_POSITION, DEBUG_COLOR_TREE, DEBUG_COLOR_BITS, DEBUG_MIN_COLOR, DEBUG_MAX_COLOR, DEBUG_WEIGHT = range(8)
