@@ -497,7 +497,7 @@ struct hdt_ctx {
     cudaStream_t side = nullptr;        // beam kernels run here, concurrently with the per-ray kernels
     cudaEvent_t fork[2] = {}, setupDone[2] = {}, join[2] = {}, traceDone[2] = {};   // per pass; traceDone[0] also gates the prefetch
     bool useBeams = true;
-    bool l2Persist = true;              // HDT_OPT_L2_PERSIST: page table of a plain HashDAG pinned in L2 (access policy window)
+    bool l2Persist = false;             // HDT_OPT_L2_PERSIST: page table of a plain HashDAG pinned in L2 (access policy window); measured slower, off
     const void* l2Window = nullptr;     // what the streams' access policy window currently covers
     size_t l2WindowBytes = 0;
     bool beamPrefetch = false;
@@ -715,9 +715,11 @@ ShadowParams make_shadow(float bias, float fog)
 u32 next_beam_tag(hdt_ctx* c) { return c->beamTag = (c->beamTag + 1) % 0x3FFFFFFFu; }
 
 // A plain HashDAG (HDT_DAG_HASH, what a drop-in caller passes) is traced through its page table: one 4-byte entry per node
-// visited, scattered over 16 MiB at depth 17 (hash_table.h:156-173).  The table is declared persisting in L2 for the tracer's
-// streams (B200: 126 MB of L2), so the streaming node and leaf loads of a frame cannot evict it; the window is (re)set only
-// when the table's address or size changes.  The resolved pool does not read the page table while traversing.
+// visited, scattered over 16 MiB at depth 17 (hash_table.h:156-173).  With HDT_OPT_L2_PERSIST the table is declared persisting
+// in L2 for the tracer's streams (cudaAccessPolicyWindow), so the streaming node and leaf loads of a frame cannot evict it; the
+// window is (re)set only when the table's address or size changes.  MEASURED on B200 (profiles/r2_ab.md): +4.6 % on the paths
+// pass, +4.9 % shadows -- the 126 MB L2 keeps the table resident anyway and the set-aside only shrinks what the nodes can use --
+// so the option is OFF by default.  (The resolved pool does not read the page table while traversing.)
 int pin_page_table(hdt_ctx* c, const DagArg& d, uint32_t pageTableEntries)
 {
     const void* base = (d.kind == HDT_DAG_HASH && c->l2Persist) ? static_cast<const void*>(d.hash.pageTable) : nullptr;

@@ -131,9 +131,9 @@ enum {
                                     records, per hit pixel, where the path leaves each ancestor below the colour tree, and trace_colors of the
                                     SAME DAG (same resolved pool, prefix pool and root) reads the voxel's colour index off those records
                                     instead of walking the DAG again.  0: always the full walk of tracer.cu:300-430. */
-    HDT_OPT_L2_PERSIST = 8,      /* default 1 (env HDT_L2_PERSIST).  A plain HashDAG (HDT_DAG_HASH) is traced through its page table (16 MiB at
-                                    depth 17, hash_table.h:156-173): the table is declared persisting in L2 for the tracer's streams
-                                    (cudaAccessPolicyWindow), so a frame's streaming node loads cannot evict it.  No effect on the other DAG kinds. */
+    HDT_OPT_L2_PERSIST = 8,      /* default 0 (env HDT_L2_PERSIST).  1: the page table of a plain HashDAG (HDT_DAG_HASH; 16 MiB at depth 17,
+                                    hash_table.h:156-173) is declared persisting in L2 for the tracer's streams (cudaAccessPolicyWindow).
+                                    Measured on B200: 4-5 % SLOWER (the 126 MB L2 keeps the table resident without help), hence off. */
     HDT_OPT_EXCHANGE_TIMEOUT_MS = 7 /* how long a framebuffer-exchange wait polls before it gives up and drops the frame (default 20000;
                                     0 = for ever).  A timeout is reported (HDT_ERR_STATE) by the next host-synchronising call. */
 };
