@@ -10,11 +10,15 @@
 
 #include <vector>
 
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
 #include "hdt_beam.cuh"
 #include "hdt_color_leaf.cuh"
 #include "hdt_colors.cuh"
 #include "hdt_device.cuh"
 #include "hdt_exchange.cuh"
+#include "hdt_hash_table.cuh"
 #include "hdt_region.cuh"
 #include "hdt_resolve.cuh"
 
@@ -528,6 +532,8 @@ struct hdt_ctx {
     const u32* ancForPool = nullptr; const u32* ancForPrefix = nullptr; u32 ancForRoot = 0;
     u32* physToVirt = nullptr;          // hdt_hash_dag_resolve: physical page -> virtual page (grow-only)
     size_t physToVirtPages = 0;
+    void* foaScratch = nullptr;         // hdt_find_or_add: keys, flags, staging (grow-only)
+    size_t foaScratchBytes = 0;
     void* comm = nullptr;               // ncclComm_t (hdt_comm_init, hdt_multi.cuh); null while world == 1
     u32 commRank = 0, commWorld = 1;
     void* rebuildScratch = nullptr;     // hdt_rebuild_color_leaf: ops, per-macro-block sums (grow-only)
@@ -990,6 +996,7 @@ int hdt_destroy(hdt_ctx* c)
     if (c->xTimedOut) cudaFreeHost(c->xTimedOut);
     hdt_comm_destroy(c);
     cudaFree(c->physToVirt);
+    cudaFree(c->foaScratch);
     cudaFree(c->rebuildScratch);
     if (c->stagingHost) cudaFreeHost(c->stagingHost);
     cudaFree(c->stagingDev);
@@ -1662,6 +1669,81 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
         HDT_CUDA(cudaEventElapsedTime(&b, c->ev[2], c->ev[3]));
         *ms = a + b;
     }
+    return HDT_OK;
+}
+
+int hdt_find_or_add(hdt_ctx* c, hdt_hash_table* table, uint32_t level, int leaves, const uint32_t* words_dev, const uint64_t* offsets_dev, uint32_t n_nodes,
+                    uint32_t* ptrs_out_dev, uint32_t counts_out[2])
+{
+    if (!c || !table || (!words_dev && n_nodes) || (!offsets_dev && n_nodes) || (!ptrs_out_dev && n_nodes)) return fail(HDT_ERR_ARG, "hdt_find_or_add: null argument");
+    if (!table->pool || !table->page_table || !table->bucket_sizes) return fail(HDT_ERR_ARG, "hdt_find_or_add: hash table without pool / page table / bucket sizes");
+    if (level + 2 > table->levels || (leaves != 0) != (level + 2 == table->levels)) return fail(HDT_ERR_ARG, "hdt_find_or_add: leaves live at level levels-2, interior nodes above it");
+    if (counts_out) counts_out[0] = counts_out[1] = 0;
+    if (!n_nodes) return HDT_OK;
+    if (HashTableDev::bucket_global_index(level, HashTableDev::buckets_per_level(level) - 1) >= table->n_buckets) return fail(HDT_ERR_ARG, "hdt_find_or_add: bucket_sizes shorter than the level's buckets");
+    if (HashTableDev::make_ptr(level, HashTableDev::buckets_per_level(level) - 1, HashTableDev::bucket_capacity(level) - 1) / kPageWords >= table->page_table_size)
+        return fail(HDT_ERR_ARG, "hdt_find_or_add: page table shorter than the level's buckets");
+    HDT_CUDA(cudaSetDevice(c->device));
+    HashTableDev t{ table->pool, table->page_table, table->bucket_sizes, table->page_table_size, table->levels, table->pool_top, table->pool_capacity_words };
+    // scratch: [keys in][keys out][isStart][segFirst][ptr flags: added, openedPage, pageRank, segBucket, segSize][staging 17 n][totals][cub temp]
+    const size_t n = n_nodes;
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    size_t cubSort = 0, cubSelect = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cubSort, static_cast<u64*>(nullptr), static_cast<u64*>(nullptr), int(n), 0, 64, c->stream);
+    cub::DeviceSelect::Flagged(nullptr, cubSelect, thrust::counting_iterator<u32>(0), static_cast<u32*>(nullptr), static_cast<u32*>(nullptr), static_cast<u32*>(nullptr), int(n), c->stream);
+    const size_t oKeys = 0, oKeys2 = oKeys + align(n * 8), oStart = oKeys2 + align(n * 8), oSeg = oStart + align(n * 4), oAdded = oSeg + align(n * 4);
+    const size_t oOpened = oAdded + align(n * 4), oRank = oOpened + align(n * 4), oSegBucket = oRank + align(n * 4), oSegSize = oSegBucket + align(n * 4);
+    const size_t oStage = oSegSize + align(n * 4), oTotals = oStage + align(n * 17 * 4), oCub = oTotals + 256, need = oCub + align(std::max(cubSort, cubSelect));
+    if (need > c->foaScratchBytes) {
+        HDT_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->foaScratch); c->foaScratch = nullptr; c->foaScratchBytes = 0;
+        HDT_CUDA(cudaMalloc(&c->foaScratch, need + need / 2));
+        c->foaScratchBytes = need + need / 2;
+    }
+    char* base = static_cast<char*>(c->foaScratch);
+    u64* keys = reinterpret_cast<u64*>(base + oKeys);
+    u64* keys2 = reinterpret_cast<u64*>(base + oKeys2);
+    u32* isStart = reinterpret_cast<u32*>(base + oStart);
+    u32* segFirst = reinterpret_cast<u32*>(base + oSeg);
+    u32* pageRank = reinterpret_cast<u32*>(base + oRank);
+    u32* staging = reinterpret_cast<u32*>(base + oStage);
+    u32* totals = reinterpret_cast<u32*>(base + oTotals);   // [0] pages opened, [1] nodes added, [2] segments, [3] errors
+    FoaOut out{ ptrs_out_dev, reinterpret_cast<u32*>(base + oAdded), reinterpret_cast<u32*>(base + oOpened), totals + 3,
+                reinterpret_cast<u32*>(base + oSegBucket), reinterpret_cast<u32*>(base + oSegSize) };
+    const u32 blocks = u32((n + 255) / 256);
+    HDT_CUDA(cudaMemsetAsync(totals, 0, 256, c->stream));
+    HDT_CUDA(cudaMemsetAsync(staging, 0, n * 17 * 4, c->stream));
+    foa_hash_kernel<<<blocks, 256, 0, c->stream>>>(words_dev, offsets_dev, n_nodes, level, leaves != 0, keys, totals + 3);
+    HDT_LAUNCHED("foa_hash_kernel");
+    size_t tmp = cubSort;
+    HDT_CUDA(cub::DeviceRadixSort::SortKeys(base + oCub, tmp, keys, keys2, int(n), 0, 64, c->stream));
+    foa_segments_kernel<<<blocks, 256, 0, c->stream>>>(keys2, n_nodes, isStart);
+    HDT_LAUNCHED("foa_segments_kernel");
+    tmp = cubSelect;
+    HDT_CUDA(cub::DeviceSelect::Flagged(base + oCub, tmp, thrust::counting_iterator<u32>(0), isStart, segFirst, totals + 2, int(n), c->stream));
+    u32 host[4] = { 0, 0, 0, 0 };
+    HDT_CUDA(cudaMemcpyAsync(host, totals, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    if (host[3] & 2) return fail(HDT_ERR_ARG, "hdt_find_or_add: a candidate is not a node (leaf: 2 words; interior: 1 + popc(child mask) words)");
+    const u32 nSeg = host[2];
+    foa_bucket_kernel<<<(nSeg + 63) / 64, 64, 0, c->stream>>>(t, level, leaves != 0, words_dev, offsets_dev, keys2, n_nodes, segFirst, nSeg, staging, out);
+    HDT_LAUNCHED("foa_bucket_kernel");
+    foa_pages_kernel<<<1, 1024, 0, c->stream>>>(out.openedPage, n_nodes, pageRank, totals);
+    HDT_LAUNCHED("foa_pages_kernel");
+    HDT_CUDA(cudaMemcpyAsync(host, totals, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    if (host[3]) return fail(HDT_ERR_CAPACITY, "hdt_find_or_add: a bucket would overflow (hash_table.h:461); nothing was inserted");
+    if ((u64(table->pool_top) + host[0]) * kPageWords > table->pool_capacity_words) return fail(HDT_ERR_CAPACITY, "hdt_find_or_add: the pool has no room for the pages the batch opens; nothing was inserted");
+    foa_apply_kernel<<<blocks, 256, 0, c->stream>>>(t, n_nodes, nSeg, out, pageRank);
+    HDT_LAUNCHED("foa_apply_kernel");
+    foa_commit_kernel<<<blocks, 256, 0, c->stream>>>(t, words_dev, offsets_dev, n_nodes, out, totals);
+    HDT_LAUNCHED("foa_commit_kernel");
+    HDT_CUDA(cudaMemcpyAsync(host, totals, sizeof(host), cudaMemcpyDeviceToHost, c->stream));
+    HDT_CUDA(cudaStreamSynchronize(c->stream));
+    HDT_CUDA(cudaGetLastError());
+    table->pool_top += host[0];
+    if (counts_out) { counts_out[0] = host[1]; counts_out[1] = host[0]; }
+    c->ancValid = false;
     return HDT_OK;
 }
 

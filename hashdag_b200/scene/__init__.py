@@ -52,13 +52,15 @@ def _load():
         lib.hds_terrain_height.restype = C.c_int32
         lib.hds_terrain_height.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         for name, ty in (("hds_basic_data", C.c_uint32), ("hds_enclosed_leaves", C.c_uint64),
-                         ("hds_hash_pool", C.c_uint32), ("hds_hash_page_table", C.c_uint32),
+                         ("hds_hash_pool", C.c_uint32), ("hds_hash_page_table", C.c_uint32), ("hds_hash_bucket_sizes", C.c_uint32),
                          ("hds_color_weights", C.c_uint32), ("hds_color_blocks", C.c_uint64),
                          ("hds_color_macro_blocks", C.c_uint64), ("hds_color_uncompressed", C.c_uint32),
                          ("hds_hash_color_nodes", C.c_uint32), ("hds_hash_color_offsets", C.c_uint64)):
             fn = getattr(lib, name)
             fn.restype = C.POINTER(ty)
             fn.argtypes = [C.c_void_p]
+        lib.hds_hash_bucket_count.restype = C.c_uint64
+        lib.hds_hash_bucket_count.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -81,6 +83,7 @@ class Scene:
     enclosed_leaves: np.ndarray = None   # uint64
     hash_pool: np.ndarray = None         # uint32, pool_top*512 words
     hash_page_table: np.ndarray = None   # uint32
+    hash_bucket_sizes: np.ndarray = None # uint32, words used per bucket (hash_table.h:18-35 order)
     hash_pool_top: int = 0
     hash_first_node_index: int = 0
     weights: np.ndarray = None           # uint32 (byte-swapped words)
@@ -126,6 +129,7 @@ def build_scene(levels: int, footprint_log2: int | None = None, seed: int = 1337
         if build_hash:
             sc.hash_pool = _arr(lib.hds_hash_pool(h), info.hash_pool_top * 512, np.uint32)
             sc.hash_page_table = _arr(lib.hds_hash_page_table(h), info.hash_page_table_size, np.uint32)
+            sc.hash_bucket_sizes = _arr(lib.hds_hash_bucket_sizes(h), lib.hds_hash_bucket_count(h), np.uint32)
             sc.hash_pool_top = info.hash_pool_top
             sc.hash_first_node_index = info.hash_first_node_index
         if build_colors:

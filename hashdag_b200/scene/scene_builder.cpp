@@ -907,6 +907,9 @@ const uint32_t* hds_basic_data(const hds_scene* s) { return s->basic.data(); }
 const uint64_t* hds_enclosed_leaves(const hds_scene* s) { return s->enclosed.data(); }
 const uint32_t* hds_hash_pool(const hds_scene* s) { return s->pool.data(); }
 const uint32_t* hds_hash_page_table(const hds_scene* s) { return s->pageTable.data(); }
+// fill count of every bucket, HashDagUtils::get_bucket_global_index order (hash_table.h:18-35)
+const uint32_t* hds_hash_bucket_sizes(const hds_scene* s) { return s->bucketSizes.data(); }
+uint64_t hds_hash_bucket_count(const hds_scene* s) { return s->bucketSizes.size(); }
 const uint32_t* hds_color_weights(const hds_scene* s) { return s->weights.data(); }
 const uint64_t* hds_color_blocks(const hds_scene* s) { return s->blocks.data(); }
 const uint64_t* hds_color_macro_blocks(const hds_scene* s) { return s->macroBlocks.data(); }

@@ -58,6 +58,8 @@ const uint32_t* hds_basic_data(const hds_scene* s);
 const uint64_t* hds_enclosed_leaves(const hds_scene* s);
 const uint32_t* hds_hash_pool(const hds_scene* s);        // hash_pool_top * 512 words
 const uint32_t* hds_hash_page_table(const hds_scene* s);
+const uint32_t* hds_hash_bucket_sizes(const hds_scene* s);   /* hds_hash_bucket_count() fill counts, hash_table.h:18-35 order */
+uint64_t hds_hash_bucket_count(const hds_scene* s);
 const uint32_t* hds_color_weights(const hds_scene* s);
 const uint64_t* hds_color_blocks(const hds_scene* s);
 const uint64_t* hds_color_macro_blocks(const hds_scene* s);

@@ -38,13 +38,13 @@ EXPORTS = (
     "hdt_partition_buffers", "hdt_assemble_colors", "hdt_exchange_create", "hdt_exchange_open", "hdt_exchange_block", "hdt_exchange_attach", "hdt_exchange_block_bytes", "hdt_exchange_attach_host",
     "hdt_exchange_frame", "hdt_exchange_release", "hdt_set_stream", "hdt_apply_ranges", "hdt_apply_ranges_host", "hdt_hash_dag_resolve", "hdt_rebuild_color_leaf", "hdt_get_values", "hdt_is_empty", "hdt_tracker_create", "hdt_tracker_destroy", "hdt_tracker_bucket_count", "hdt_tracker_snapshot", "hdt_tracker_delta",
     "hdt_comm_unique_id", "hdt_comm_init", "hdt_comm_destroy", "hdt_replicate", "hdt_broadcast_dirty", "hdt_broadcast_ranges",
-    "hdt_launch_count", "hdt_recorded_color_passes", "hdt_version",
+    "hdt_find_or_add", "hdt_launch_count", "hdt_recorded_color_passes", "hdt_version",
 )
-ERR_CAPACITY = 4
+ERR_ARG, ERR_CAPACITY = 1, 4   # HDT_ERR_* of include/hashdag_b200.h the tests tell apart
 
 
 class TracerError(RuntimeError):
-    pass
+    code = 0                     # the C ABI's return code
 
 
 class Range(C.Structure):     # hdt_range
@@ -60,6 +60,11 @@ class DagDeltaPod(C.Structure):   # hdt_dag_delta
 class ReplicaPod(C.Structure):    # hdt_replica
     _fields_ = [("pool", C.c_void_p), ("pool_capacity_words", C.c_uint64), ("page_table", C.c_void_p), ("page_table_size", C.c_uint32),
                 ("first_node_index", C.c_uint32), ("pool_top", C.c_uint32), ("resolved_pool", C.c_void_p), ("prefix_pool", C.c_void_p)]
+
+
+class HashTablePod(C.Structure):   # hdt_hash_table
+    _fields_ = [("pool", C.c_void_p), ("pool_capacity_words", C.c_uint64), ("page_table", C.c_void_p), ("page_table_size", C.c_uint32),
+                ("bucket_sizes", C.c_void_p), ("n_buckets", C.c_uint32), ("pool_top", C.c_uint32), ("levels", C.c_uint32)]
 
 
 class ToolInfo(C.Structure):  # tracer.h:33-39
@@ -132,6 +137,7 @@ def load_library():
     lib.hdt_replicate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
     lib.hdt_broadcast_dirty.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(DagDeltaPod), C.POINTER(ReplicaPod)]
     lib.hdt_broadcast_ranges.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    lib.hdt_find_or_add.argtypes = [C.c_void_p, C.POINTER(HashTablePod), C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
     lib.hdt_launch_count.restype = C.c_uint64
     lib.hdt_launch_count.argtypes = [C.c_void_p]
     lib.hdt_recorded_color_passes.restype = C.c_uint64
@@ -142,7 +148,9 @@ def load_library():
 
 def _check(rc):
     if rc != 0:
-        raise TracerError(f"hashdag_b200 error {rc}: {load_library().hdt_last_error().decode()}")
+        err = TracerError(f"hashdag_b200 error {rc}: {load_library().hdt_last_error().decode()}")
+        err.code = rc
+        raise err
 
 
 def _torch():
@@ -578,6 +586,28 @@ class DAGTracer:
         payload = np.ascontiguousarray(payload, dtype=np.uint32)
         ranges = np.ascontiguousarray(ranges)
         _check(self._lib.hdt_broadcast_ranges(self._ctx, root, dst_tensor.data_ptr(), dst_tensor.numel(), payload.ctypes.data, payload.size, ranges.ctypes.data, len(ranges)))
+
+    # -- GPU batch insert into the hash table (HashTable::find_or_add_*, hash_table.h:470-560) -----------
+    def find_or_add(self, table: HashTablePod, level: int, nodes, leaves: bool = False):
+        """hdt_find_or_add: `nodes` = list of uint32 arrays (interior: [header, child pointers...]; leaf: 2 words) of ONE level in
+        insertion order.  -> (virtual pointers uint32[n], nodes added, pages opened); `table` (device arrays) is updated in place."""
+        torch = _torch()
+        dev = f"cuda:{self.device}"
+        sizes = np.array([len(w) for w in nodes], dtype=np.int64)
+        offsets = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+        words = np.concatenate([np.asarray(w, dtype=np.uint32) for w in nodes]) if len(nodes) else np.zeros(1, np.uint32)
+        ptrs, added, pages = self.find_or_add_device(table, level, _to_device(words, dev), torch.from_numpy(offsets).to(dev), len(nodes), leaves)
+        return ptrs.cpu().numpy().view(np.uint32), added, pages
+
+    def find_or_add_device(self, table: HashTablePod, level: int, words, offsets, n_nodes: int, leaves: bool = False):
+        """hdt_find_or_add on device tensors: node i = words[offsets[i]:offsets[i+1]] (int32 words, int64 offsets[n+1]).
+        -> (int32 tensor of virtual pointers, nodes added, pages opened)."""
+        torch = _torch()
+        ptrs = torch.empty(max(1, n_nodes), dtype=torch.int32, device=words.device)
+        counts = (C.c_uint32 * 2)()
+        torch.cuda.synchronize()
+        _check(self._lib.hdt_find_or_add(self._ctx, C.byref(table), int(level), int(bool(leaves)), _ptr(words), offsets.data_ptr(), int(n_nodes), ptrs.data_ptr(), counts))
+        return ptrs[:n_nodes], int(counts[0]), int(counts[1])
 
     def rebuild_color_leaf(self, ops: np.ndarray, old_leaf: "CompressedColorLeaf | None" = None, device=None):
         """Re-encode a colour leaf on the GPU from an op list (color_leaf.OP_DTYPE records = hdt_color_op), see

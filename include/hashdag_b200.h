@@ -263,6 +263,26 @@ int hdt_get_values(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_p
 int hdt_is_empty(hdt_ctx* ctx, int dag_kind, const void* dag_pod, size_t dag_pod_size, uint32_t max_level, const uint32_t start[3],
                  const uint32_t size[3], int* empty, float* ms);
 
+/* GPU batch insert into the hash table: HashTable::find_or_add_interior_node / find_or_add_leaf_node
+ * (hash_table.h:470-560) for n_nodes candidate nodes of ONE level, given in insertion order -- node i is
+ * words_dev[offsets_dev[i] .. offsets_dev[i+1]) (DEVICE; an interior node = [header][virtual child pointers], 2..9 words; a leaf
+ * = its 64 bits as two words; `leaves` != 0 iff level == levels-2).  ptrs_out_dev[i] (DEVICE) receives the node's virtual pointer,
+ * and pool, page table, bucket fill counts and pool_top end up exactly as if the reference had been handed the nodes one
+ * after the other (same search order and node-boundary rule, same page padding, physical pages in insertion order; its
+ * Bloom filter never changes a result and has no counterpart).  Pool words no node occupies are taken to be zero.
+ * `table`: device arrays owned by the caller; bucket_sizes in HashDagUtils::get_bucket_global_index order (hash_table.h:18-35).
+ * counts_out = {nodes added, pages opened}.  HDT_ERR_CAPACITY if a bucket or the pool would overflow: nothing is inserted.
+ * Synchronous. */
+typedef struct hdt_hash_table {
+    uint32_t* pool; uint64_t pool_capacity_words;
+    uint32_t* page_table; uint32_t page_table_size;
+    uint32_t* bucket_sizes; uint32_t n_buckets;
+    uint32_t pool_top;          /* in/out */
+    uint32_t levels;
+} hdt_hash_table;
+int hdt_find_or_add(hdt_ctx* ctx, hdt_hash_table* table, uint32_t level, int leaves, const uint32_t* words_dev, const uint64_t* offsets_dev, uint32_t n_nodes,
+                    uint32_t* ptrs_out_dev, uint32_t counts_out[2]);
+
 /* hdt_apply_ranges with `ranges` and `payload` in HOST memory (pageable is fine): both are staged through pinned memory
  * owned by the context, copied and applied in stream order.  Returns once the copy and the kernel are enqueued --
  * frames enqueued afterwards see the edit, no host synchronisation is involved (hdt_sync() reports errors).

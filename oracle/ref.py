@@ -166,6 +166,14 @@ class RefTracer:
         """The reference's own CPU edit (SphereEditor<adding>, hash_dag_editors.h:273-313) + upload_to_gpu."""
         assert self.lib.ref_edit_sphere(float(center[0]), float(center[1]), float(center[2]), float(radius), int(bool(adding))) == 0
 
+    def find_or_add(self, level, nodes, leaves=False):
+        """The reference's HashTable::find_or_add_* (hash_table.h:470-560) for `nodes` (uint32 arrays), one after the other."""
+        offsets = np.concatenate(([0], np.cumsum([len(w) for w in nodes]))).astype(np.uint64)
+        words = np.ascontiguousarray(np.concatenate(nodes), dtype=np.uint32)
+        ptrs = np.empty(len(nodes), dtype=np.uint32)
+        assert self.lib.ref_find_or_add(int(level), int(bool(leaves)), words.ctypes.data, offsets.ctypes.data, len(nodes), ptrs.ctypes.data) == 0
+        return ptrs
+
     def last_edit_ms(self):
         """(HashDAG::edit_threads, HashTable::upload_to_gpu) host milliseconds of the last edit_sphere."""
         out = (C.c_double * 2)()

@@ -73,4 +73,17 @@ int ref_is_empty(uint32_t maxLevel, const uint32_t* start, const uint32_t* size)
     return DAGUtils::is_empty(g_hash, maxLevel, make_uint3(start[0], start[1], start[2]), make_uint3(size[0], size[1], size[2])) ? 1 : 0;
 }
 
+
+// The reference's own insert, one node after the other (HashTable::find_or_add_interior_node / find_or_add_leaf_node,
+// hash_table.h:470-560), on its host table: node i = words[offsets[i] .. offsets[i+1]); the checker of hdt_find_or_add.
+int ref_find_or_add(uint32_t level, int leaves, const uint32_t* words, const uint64_t* offsets, uint32_t n, uint32_t* ptrs)
+{
+    if (!g_hasHash) return 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t* w = words + offsets[i];
+        if (leaves) ptrs[i] = g_hash.data.find_or_add_leaf_node(level, uint64_t(w[0]) | (uint64_t(w[1]) << 32));
+        else ptrs[i] = g_hash.data.find_or_add_interior_node(level, uint32_t(offsets[i + 1] - offsets[i]), w);
+    }
+    return 0;
+}
 }  // extern "C"

@@ -7,6 +7,7 @@
 #   launches                  ncu launch list of a short bench run (per-launch device times, cold caches)
 #   ncu                       ncu --set full of the three per-pixel kernels of a short bench run
 #   smoke                     __graft_entry__.smoke()
+#   golden <generator.py>     a tests/golden/make_*.py fixture generator (reference harness) -> gpurun_out/golden/
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -28,6 +29,8 @@ ncu)
     ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_raw.csv 2>/dev/null ;;
 smoke)
     python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/${TAG}_smoke.log ;;
+golden)
+    timeout 900 python "$1" gpurun_out/golden 2>&1 | tail -20 | tee gpurun_out/${TAG}_golden.log ;;
 *)
     echo "unknown stage $stage"; exit 2 ;;
 esac
