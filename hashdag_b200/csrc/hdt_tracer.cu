@@ -1643,7 +1643,7 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     u64* dTotals = reinterpret_cast<u64*>(base + offTotals);
     HDT_CUDA(cudaMemcpyAsync(dOps, dev.data(), dev.size() * sizeof(ColorOpDev), cudaMemcpyHostToDevice, c->stream));
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    count_color_ops_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, dTiles);
+    color_pieces_kernel<false><<<nTiles, kPieceThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, dTiles, nullptr, nullptr, nullptr, nullptr);
     scan_color_tiles_kernel<<<1, 1024, 0, c->stream>>>(dTiles, nTiles, dOffsets, dTotals);
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->launches += 2;
@@ -1658,7 +1658,7 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     if ((counts_out[1] && !weights_out) || !blocks_out || !macro_blocks_out) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: null output buffer");
     HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (counts_out[1]) HDT_CUDA(cudaMemsetAsync(weights_out, 0, counts_out[1] * sizeof(u32), c->stream));
-    emit_color_leaf_kernel<<<nTiles, kRebuildThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, dOffsets, weights_out, blocks_out, macro_blocks_out);
+    color_pieces_kernel<true><<<nTiles, kPieceThreads, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, nullptr, dOffsets, weights_out, blocks_out, macro_blocks_out);
     HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));

@@ -77,6 +77,31 @@ def test_copy_and_fill_ops_from_a_unique_and_a_shared_leaf(t):
         assert ms > 0
 
 
+def test_long_runs_with_weights_and_short_copies(t):
+    # pieces (runs of one old block / one FILL) of every length: repeated weights of each width over several macro blocks
+    # (periodic bit patterns, 3 bits does not divide a word), copies of a few colours each, copies over old macro boundaries
+    scene = gu.recipe_scene("d13")
+    old_host = (scene.weights, scene.blocks, scene.macro_blocks)
+    n = int(scene.n_voxels)
+    rng = np.random.default_rng(77)
+    rows = []
+    for bpw, count in ((3, 5000), (1, 40001), (4, 16384), (2, 7), (3, 33333), (0, 20000), (4, 1)):
+        rows.append((0, count, host.OP_FILL, bpw, int(rng.integers(0, 1 << 32)), int(rng.integers(0, 1 << bpw))))
+        src = int(rng.integers(0, n - 40000))
+        rows.append((src, int(rng.integers(1, 40)), host.OP_COPY, 0, 0, 0))
+        rows.append((16384 * int(rng.integers(1, n // 16384 - 2)) - 11, 30000, host.OP_COPY, 0, 0, 0))
+    for k in range(700):       # more segments in one macro block than a CTA has threads
+        rows.append((int(rng.integers(0, n - 5000)), int(rng.integers(1, 30)), host.OP_COPY, 0, 0, 0))
+        rows.append((0, int(rng.integers(1, 4)), host.OP_FILL, 2, 0xABC00000 + k % 3, k % 4))
+    ops = np.array(rows, dtype=host.OP_DTYPE)
+    for offset in (None, 4097):
+        old = tracer.CompressedColorLeaf.from_scene(scene)
+        if offset is not None:
+            old.offset = offset
+        leaf, _ = t.rebuild_color_leaf(ops, old)
+        assert_same(to_host(leaf), cl.rebuild(ops.astype(cl.OP_DTYPE), old_host + (offset,)), f"offset={offset}")
+
+
 @pytest.mark.parametrize("recipe", ["d13", "d17"])
 def test_reference_leaves_survive_decode_and_reencode(t, recipe):
     """COPY(0, n) of a leaf the reference built must give that leaf back, byte for byte."""
