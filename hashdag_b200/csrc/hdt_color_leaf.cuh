@@ -32,7 +32,7 @@
 namespace hdt {
 
 constexpr u32 kPieceThreads = 256;
-constexpr u32 kLongPieceWords = 12;   // pieces whose weights span more words than this are copied by the whole CTA
+constexpr u32 kPiecesPerThread = 4;
 
 // hdt_color_op with the exclusive prefix of the counts (where the op's first colour lands in the new leaf).
 struct ColorOpDev { u64 dstStart; u64 srcStart; u32 kind; u32 bitsPerWeight; u32 colorBits; u32 weight; };
@@ -40,30 +40,31 @@ static_assert(sizeof(ColorOpDev) == 32, "uploaded as is");
 
 struct TilePair { u32 blocks; u32 bits; };   // per macro block: blocks started, weight bits appended
 
-__device__ __forceinline__ u64 cta_exclusive_scan(u64 v, u64& total)
+template<typename V>
+__device__ __forceinline__ V cta_exclusive_scan(V v, V& total)
 {
-    __shared__ u64 warpSums[32];
+    __shared__ V warpSums[32];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 inc = v;
+    V inc = v;
 #pragma unroll
     for (u32 d = 1; d < 32; d <<= 1) {
-        const u64 o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        const V o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
         if (lane >= d) inc += o;
     }
     if (lane == 31) warpSums[warp] = inc;
     __syncthreads();
     if (warp == 0) {
         const u32 nWarps = blockDim.x >> 5;
-        u64 w = lane < nWarps ? warpSums[lane] : 0;
+        V w = lane < nWarps ? warpSums[lane] : V(0);
 #pragma unroll
         for (u32 d = 1; d < 32; d <<= 1) {
-            const u64 o = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            const V o = __shfl_up_sync(0xFFFFFFFFu, w, d);
             if (lane >= d) w += o;
         }
         warpSums[lane] = w;   // inclusive over warps
     }
     __syncthreads();
-    const u64 base = warp ? warpSums[warp - 1] : 0;
+    const V base = warp ? warpSums[warp - 1] : V(0);
     total = warpSums[(blockDim.x >> 5) - 1];
     __syncthreads();          // warpSums may be reused by the caller's next scan
     return base + inc - v;
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(1024) scan_color_tiles_kernel(const TilePair* 
         const u32 m = base + threadIdx.x;
         const TilePair t = m < nTiles ? tiles[m] : TilePair{ 0, 0 };
         u64 totB, totW;
-        const u64 eb = cta_exclusive_scan(t.blocks, totB);
-        const u64 ew = cta_exclusive_scan(t.bits, totW);
+        const u64 eb = cta_exclusive_scan(u64(t.blocks), totB);
+        const u64 ew = cta_exclusive_scan(u64(t.bits), totW);
         if (m < nTiles) offsets[m] = make_ulonglong2(carryBlocks + eb, carryBits + ew);
         carryBlocks += totB; carryBits += totW;
     }
@@ -108,65 +109,66 @@ __device__ __forceinline__ u32 find_block(const ColorLeafDev& l, u32 macro, u32 
     return lo;
 }
 
-// Where a piece's weight bits come from: a bit position of the old stream, or (FILL) the first 64 bits of a periodic pattern.
-struct BitSource {
-    u64 at;        // COPY: absolute bit position in the old leaf's stream; FILL: the pattern, first bit in bit 63
-    u32 period;    // 0: COPY; else bitsPerWeight of the FILL
-};
-
-// `take` (1..32) bits starting `skip` bits into the piece, left-aligned in the result.
-__device__ __forceinline__ u32 read_bits(const ColorLeafDev& l, const BitSource& src, u32 skip, u32 take)
+// The same search by a whole warp, 32 probes at a time: two or three dependent loads instead of ten.  All lanes get the result.
+__device__ __forceinline__ u32 find_block_warp(const ColorLeafDev& l, u32 macro, u32 local, u32& lastBlock)
 {
-    u32 v;
-    if (src.period) {
-        v = u32((src.at << (skip % src.period)) >> 32);
-    } else {
-        const u64 p = src.at + skip;
-        const u64 wi = p >> 5;
-        const u32 sh = u32(p) & 31;
-        const u32 hi = wi < l.nWeights ? __byte_perm(__ldg(l.weights + wi), 0, 0x0123) : 0u;
-        const u32 lo = (sh + take > 32 && wi + 1 < l.nWeights) ? __byte_perm(__ldg(l.weights + wi + 1), 0, 0x0123) : 0u;
-        v = __funnelshift_l(lo, hi, sh);
+    const u32 lane = threadIdx.x & 31;
+    u32 lo = u32(__ldg(l.macroBlocks + 2 * u64(macro)));
+    lastBlock = (2 * (u64(macro) + 1) < l.nMacroWords) ? u32(__ldg(l.macroBlocks + 2 * (u64(macro) + 1)) - 1) : u32(l.nBlocks - 1);
+    u32 hi = lastBlock;                         // blocks[lo] starts at colour 0 <= local: the answer is in [lo, hi]
+    while (hi - lo >= 32) {
+        const u32 step = (hi - lo) / 32;        // probes lo + step, lo + 2 step, ... lo + 32 step (<= hi)
+        const u32 probe = lo + (lane + 1) * step;
+        const u32 below = __popc(__ballot_sync(0xFFFFFFFFu, (u32(__ldg(l.blocks + probe)) & 0x3FFF) <= local));   // starts increase: a prefix of the lanes
+        const u32 newLo = lo + below * step;
+        hi = below == 32 ? hi : newLo + step - 1;
+        lo = newLo;
     }
-    return v & (0xFFFFFFFFu << (32 - take));
+    const bool ok = lo + lane <= hi && (u32(__ldg(l.blocks + lo + lane)) & 0x3FFF) <= local;
+    return lo + __popc(__ballot_sync(0xFFFFFFFFu, ok)) - 1;
 }
 
-// Bits [q, q + n) of the macro block's stream (`words`, shared, MSB-first, zeroed) <- the piece's bits; the destination words
-// j = first, first + stride, ... of the range are handled by the caller (one thread: 0, 1; the CTA: threadIdx.x, blockDim.x).
-__device__ __forceinline__ void write_bits(u32* words, const ColorLeafDev& l, const BitSource& src, u32 q, u32 n, u32 first, u32 stride)
+// `take` (1..32) bits of the old leaf's weight stream from bit position `p`, left-aligned in the result.
+__device__ __forceinline__ u32 read_stream_bits(const ColorLeafDev& l, u64 p, u32 take)
 {
-    const u32 w0 = q >> 5, nWords = ((q + n - 1) >> 5) - w0 + 1;
-    for (u32 j = first; j < nWords; j += stride) {
-        const u32 ws = (w0 + j) << 5;
-        const u32 a = max(q, ws), b = min(q + n, ws + 32);
-        const u32 v = read_bits(l, src, a - q, b - a);
-        if (b - a == 32) words[w0 + j] = v;          // the word belongs to this piece alone
-        else atomicOr(&words[w0 + j], v >> (a & 31));
-    }
+    const u64 wi = p >> 5;
+    const u32 sh = u32(p) & 31;
+    const u32 hi = wi < l.nWeights ? __byte_perm(__ldg(l.weights + wi), 0, 0x0123) : 0u;
+    const u32 lo = (sh + take > 32 && wi + 1 < l.nWeights) ? __byte_perm(__ldg(l.weights + wi + 1), 0, 0x0123) : 0u;
+    return __funnelshift_l(lo, hi, sh) & (0xFFFFFFFFu << (32 - take));
 }
+
+// One piece: what a thread keeps of it between the two halves of a round.
+struct Piece { u64 key; u32 dstLocal; u32 bits; };
 
 // One CTA per macro block of the new leaf.  EMIT = false: tiles[blockIdx] = {blocks started, weight bits}.  EMIT = true: the
-// macro block is written (offsets[blockIdx] = its first block index and weight bit offset).
+// macro block is written (offsets[blockIdx] = its first block index and weight bit offset; `weights` zeroed beforehand).
+//
+// The ops that reach into the macro block are taken T at a time (a "chunk" of segments, one per thread: where the segment's
+// colours come from, how many pieces it has), the pieces of a chunk T*K at a time (a "round": K consecutive pieces per thread,
+// one CTA-wide scan of {blocks started, weight bits}).  The weights are not moved piece by piece: the pieces of a COPY segment
+// are consecutive blocks of the old leaf, so the segment's weights are ONE contiguous bit range of the old stream, and a FILL
+// segment is a periodic pattern.  After the rounds of a chunk every destination word of the chunk's bit range is put together
+// by one thread from the segments that overlap it (funnel shifts) and stored once.
 template<bool EMIT>
 __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const ColorOpDev* __restrict__ ops, const u32 nOps, const ColorLeafDev oldLeaf, const u64 nColors,
                                                                       TilePair* __restrict__ tiles, const ulonglong2* __restrict__ offsets,
                                                                       u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
 {
-    constexpr u32 T = kPieceThreads;
-    // the segments (op x this macro block) of the current chunk, one per thread
+    constexpr u32 T = kPieceThreads, K = kPiecesPerThread;
     __shared__ u32 segPieceStart[T + 1];    // exclusive prefix of the pieces per segment
     __shared__ u32 segDst[T], segLen[T], segBlock0[T], segLast0[T];
     __shared__ u64 segSrc[T];
-    __shared__ u64 pieceKey[T];
-    // a macro block holds at most 16384 * 4 weight bits = 2048 words, + 1 for the misaligned start
-    __shared__ u32 words[EMIT ? kColorsPerMacroBlock * 4 / 32 + 2 : 1];
-    __shared__ u32 longCount;
-    __shared__ u32 longQ[EMIT ? T : 1], longN[EMIT ? T : 1], longPeriod[EMIT ? T : 1];
-    __shared__ u64 longAt[EMIT ? T : 1];
+    __shared__ u64 lastKeyOf[T];            // key of each thread's last piece of the round
+    // weight bits of the segments, relative to the macro block: bits [segBit0, segMid) come from the old stream at (bit + segDelta[0]),
+    // bits [segMid, segBit1) from (bit + segDelta[1]) -- a segment spans at most two macro blocks of the old leaf, and the stream of
+    // the old leaf need not be contiguous across them (the format lets a builder pad there)
+    __shared__ u32 segBit0[EMIT ? T : 1], segMid[EMIT ? T : 1], segBit1[EMIT ? T : 1];
+    __shared__ u64 segDelta[EMIT ? 2 : 1][EMIT ? T : 1];
 
     const u32 t = threadIdx.x;
     const u64 d0 = u64(blockIdx.x) * kColorsPerMacroBlock, d1 = min(d0 + kColorsPerMacroBlock, nColors);
-    // ops that reach into [d0, d1): lo = last op starting at or before d0, hi = last op starting before d1
+    // ops that reach into [d0, d1): lo = last op starting at or before d0, last = last op starting before d1
     u32 lo = 0, hi = nOps - 1;
     while (lo < hi) {
         const u32 mid = (lo + hi + 1) >> 1;
@@ -182,11 +184,8 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
     const u64 sharedOffset = oldLeaf.is_shared() ? oldLeaf.offset : 0;
 
     ulonglong2 tile = make_ulonglong2(0, 0);
-    u32 skew = 0;
     if (EMIT) {
         tile = offsets[blockIdx.x];
-        skew = u32(tile.y & 31);
-        for (u32 k = t; k < sizeof(words) / 4; k += T) words[k] = 0;
         if (t == 0) {   // MacroBlockStruct, vwsc.h:595-599 / build() :677-681
             macroBlocks[2 * u64(blockIdx.x)] = tile.x;
             macroBlocks[2 * u64(blockIdx.x) + 1] = tile.y;
@@ -197,119 +196,191 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
 
     for (u32 segBase = 0; segBase < nSeg; segBase += T) {
         const u32 nChunk = min(T, nSeg - segBase);
+        const u32 chunkBit0 = carryBits;
         // ---- segments of this chunk ----
+        // (a few segments: one warp each, searching with 32 probes at a time; many: one thread each)
         u32 myPieces = 0;
-        if (t < nChunk) {
-            const ColorOpDev op = ops[lo + segBase + t];
-            const u64 a = max(op.dstStart, d0), b = min(__ldg(&ops[lo + segBase + t + 1].dstStart), d1);
-            segDst[t] = u32(a - d0);
-            segLen[t] = u32(b - a);
+        const bool byWarp = nChunk <= T / 32;
+        const u32 mySeg = byWarp ? t / 32 : t;
+        if (mySeg < nChunk) {
+            const ColorOpDev op = ops[lo + segBase + mySeg];
+            const u64 a = max(op.dstStart, d0), b = min(__ldg(&ops[lo + segBase + mySeg + 1].dstStart), d1);
+            u64 s0 = 0;
+            u32 b0 = 0, last0 = 0;
             myPieces = 1;
             if (op.kind == HDT_COLOR_OP_COPY) {
-                const u64 s0 = op.srcStart + (a - op.dstStart) + sharedOffset, s1 = s0 + (b - a) - 1;
-                u32 last0, last1;
-                const u32 b0 = find_block(oldLeaf, u32(s0 / kColorsPerMacroBlock), u32(s0 % kColorsPerMacroBlock), last0);
-                const u32 b1 = find_block(oldLeaf, u32(s1 / kColorsPerMacroBlock), u32(s1 % kColorsPerMacroBlock), last1);
-                segSrc[t] = s0; segBlock0[t] = b0; segLast0[t] = last0;
+                s0 = op.srcStart + (a - op.dstStart) + sharedOffset;
+                const u64 s1 = s0 + (b - a) - 1;
+                u32 last1, b1;
+                if (byWarp) {
+                    b0 = find_block_warp(oldLeaf, u32(s0 / kColorsPerMacroBlock), u32(s0 % kColorsPerMacroBlock), last0);
+                    b1 = find_block_warp(oldLeaf, u32(s1 / kColorsPerMacroBlock), u32(s1 % kColorsPerMacroBlock), last1);
+                } else {
+                    b0 = find_block(oldLeaf, u32(s0 / kColorsPerMacroBlock), u32(s0 % kColorsPerMacroBlock), last0);
+                    b1 = find_block(oldLeaf, u32(s1 / kColorsPerMacroBlock), u32(s1 % kColorsPerMacroBlock), last1);
+                }
                 myPieces = b1 - b0 + 1;
             }
+            if (!byWarp || (t & 31) == 0) {
+                segDst[mySeg] = u32(a - d0); segLen[mySeg] = u32(b - a);
+                segSrc[mySeg] = s0; segBlock0[mySeg] = b0; segLast0[mySeg] = last0;
+                if (byWarp) segPieceStart[mySeg] = myPieces;   // handed to thread mySeg for the scan below
+            }
         }
-        u64 totalPieces64;
-        const u32 myStart = u32(cta_exclusive_scan(myPieces, totalPieces64));
-        const u32 totalPieces = u32(totalPieces64);
+        if (byWarp) {
+            __syncthreads();
+            myPieces = t < nChunk ? segPieceStart[t] : 0;
+            __syncthreads();
+        }
+        u32 totalPieces;
+        const u32 myStart = cta_exclusive_scan(myPieces, totalPieces);
         if (t < nChunk) segPieceStart[t] = myStart;
-        if (t == 0) { segPieceStart[nChunk] = totalPieces; if (EMIT) longCount = 0; }
+        if (t == 0) segPieceStart[nChunk] = totalPieces;
         __syncthreads();
-        // ---- pieces of this chunk, T at a time ----
-        for (u32 pBase = 0; pBase < totalPieces; pBase += T) {
-            const u32 p = pBase + t;
-            const bool valid = p < totalPieces;
-            u64 key = 0;
-            u32 dstLocal = 0, len = 0, bpw = 0;
-            BitSource src{ 0, 0 };
-            if (valid) {
-                u32 s = 0, e = nChunk - 1;       // segment of piece p: last one starting at or before p
+        // ---- pieces of this chunk, T * K at a time ----
+        for (u32 pBase = 0; pBase < totalPieces; pBase += T * K) {
+            const u32 p0 = pBase + t * K;
+            u32 s = 0;                           // segment of piece p0: last one starting at or before it
+            if (nChunk > 1 && p0 < totalPieces) {
+                u32 e = nChunk - 1;
                 while (s < e) {
                     const u32 mid = (s + e + 1) >> 1;
-                    if (segPieceStart[mid] <= p) s = mid; else e = mid - 1;
+                    if (segPieceStart[mid] <= p0) s = mid; else e = mid - 1;
                 }
-                const ColorOpDev op = ops[lo + segBase + s];
-                if (op.kind == HDT_COLOR_OP_COPY) {
-                    const u32 b = segBlock0[s] + (p - segPieceStart[s]);
-                    const u64 s0 = segSrc[s], s1 = s0 + segLen[s];
-                    const u64 macro = s0 / kColorsPerMacroBlock + (b > segLast0[s] ? 1 : 0);   // a segment spans at most two old macro blocks
-                    const u64 blk = __ldg(oldLeaf.blocks + b);
-                    const u32 hdr = u32(blk), startLocal = hdr & 0x3FFF;
-                    const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
-                    const u64 blockStart = macro * kColorsPerMacroBlock + startLocal;
-                    // starts increase inside a macro block: a smaller or equal one belongs to the next macro block
-                    const u64 blockEnd = macro * kColorsPerMacroBlock + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
-                    const u64 ps = max(blockStart, s0), pe = min(blockEnd, s1);
-                    bpw = block_bits_per_weight(hdr);
-                    key = (blk >> 32) | (u64(bpw) << 32);
-                    dstLocal = segDst[s] + u32(ps - s0);
-                    len = u32(pe - ps);
-                    if (EMIT && bpw) src.at = __ldg(oldLeaf.macroBlocks + 2 * macro + 1) + (hdr >> 16) + (ps - blockStart) * bpw;
-                } else {
-                    bpw = op.bitsPerWeight;
-                    key = u64(op.colorBits) | (u64(bpw) << 32);
-                    dstLocal = segDst[s];
-                    len = segLen[s];
-                    if (EMIT && bpw) {           // the stream of a repeated weight: its first 64 bits
+            }
+            Piece pc[K];
+            u64 srcAt[EMIT ? K : 1];
+            u32 myBits = 0, secondHalf = 0;      // bit j: piece j lies in the second old macro block of its segment
+#pragma unroll
+            for (u32 j = 0; j < K; ++j) {
+                const u32 p = p0 + j;
+                pc[j].key = 0; pc[j].dstLocal = 0; pc[j].bits = 0;
+                if (EMIT) srcAt[j] = 0;
+                if (p < totalPieces) {
+                    while (p >= segPieceStart[s + 1]) ++s;
+                    const ColorOpDev op = ops[lo + segBase + s];
+                    if (op.kind == HDT_COLOR_OP_COPY) {
+                        const u32 b = segBlock0[s] + (p - segPieceStart[s]);
+                        const u64 s0 = segSrc[s], s1 = s0 + segLen[s];
+                        const u64 macroBase = (s0 / kColorsPerMacroBlock + (b > segLast0[s] ? 1 : 0)) * kColorsPerMacroBlock;   // a segment spans at most two old macro blocks
+                        const u64 blk = __ldg(oldLeaf.blocks + b);
+                        const u32 hdr = u32(blk), startLocal = hdr & 0x3FFF;
+                        const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
+                        // starts increase inside a macro block: a smaller or equal one belongs to the next macro block
+                        const u64 blockStart = macroBase + startLocal, blockEnd = macroBase + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
+                        const u64 ps = max(blockStart, s0), pe = min(blockEnd, s1);
+                        const u32 bpw = block_bits_per_weight(hdr);
+                        pc[j].key = (blk >> 32) | (u64(bpw) << 32);
+                        pc[j].dstLocal = segDst[s] + u32(ps - s0);
+                        pc[j].bits = u32(pe - ps) * bpw;
+                        if (EMIT && bpw) srcAt[j] = __ldg(oldLeaf.macroBlocks + 2 * (macroBase / kColorsPerMacroBlock) + 1) + (hdr >> 16) + (ps - blockStart) * bpw;
+                        if (EMIT && b > segLast0[s]) secondHalf |= (b == segLast0[s] + 1 ? 0x101u : 0x1u) << j;   // (bit 8 + j: the first such piece)
+                    } else {
+                        pc[j].key = u64(op.colorBits) | (u64(op.bitsPerWeight) << 32);
+                        pc[j].dstLocal = segDst[s];
+                        pc[j].bits = segLen[s] * op.bitsPerWeight;
+                    }
+                    myBits += pc[j].bits;
+                }
+            }
+            const u32 nMine = p0 >= totalPieces ? 0u : min(K, totalPieces - p0);
+            if (nMine) {
+                u64 k = pc[0].key;
+#pragma unroll
+                for (u32 j = 1; j < K; ++j) if (j < nMine) k = pc[j].key;
+                lastKeyOf[t] = k;
+            }
+            __syncthreads();
+            u64 prevKey = t ? lastKeyOf[t - 1] : carryKey;      // (threads in front of a thread that has pieces have K each)
+            u32 startsMask = 0;
+#pragma unroll
+            for (u32 j = 0; j < K; ++j) {
+                if (j < nMine && (pc[j].dstLocal == 0 || pc[j].key != prevKey)) startsMask |= 1u << j;   // ColorLeafBuilder::add, vwsc.h:606
+                prevKey = pc[j].key;
+            }
+            // {blocks started, weight bits} in one word: a macro block has at most 65536 bits, a round at most T * K pieces
+            static_assert(T * K < 4096, "12 bits for the blocks a round starts");
+            u32 total;
+            const u32 excl = cta_exclusive_scan((u32(__popc(startsMask)) << 20) | myBits, total);
+            const u32 nInRound = min(T * K, totalPieces - pBase);
+            const u64 roundLastKey = lastKeyOf[(nInRound - 1) / K];
+            if (EMIT && nMine) {
+                u64 blockIndex = tile.x + carryBlocks + (excl >> 20);
+                u32 bit = carryBits + (excl & 0xFFFFF);     // weight bit offset relative to the macro block
+                s = 0;
+                if (nChunk > 1) {
+                    u32 e = nChunk - 1;
+                    while (s < e) {
+                        const u32 mid = (s + e + 1) >> 1;
+                        if (segPieceStart[mid] <= p0) s = mid; else e = mid - 1;
+                    }
+                }
+#pragma unroll
+                for (u32 j = 0; j < K; ++j) {
+                    if (j < nMine) {
+                        const u32 p = p0 + j;
+                        while (p >= segPieceStart[s + 1]) ++s;
+                        const u32 bpw = u32(pc[j].key >> 32);
+                        if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(u32(pc[j].key)) << 32) | make_block_header(bit, bpw, pc[j].dstLocal);
+                        const u32 half = (secondHalf >> j) & 1;
+                        if (p == segPieceStart[s]) segBit0[s] = bit;
+                        if (secondHalf & (0x100u << j)) segMid[s] = bit;
+                        if (pc[j].bits) segDelta[half][s] = srcAt[j] - bit;           // the same for every piece of the half (FILL: unused)
+                        bit += pc[j].bits;
+                        if (p + 1 == segPieceStart[s + 1]) {
+                            segBit1[s] = bit;
+                            if (!half) segMid[s] = bit;                               // no second half
+                        }
+                    }
+                }
+            }
+            carryBlocks += total >> 20;
+            carryBits += total & 0xFFFFF;
+            carryKey = roundLastKey;
+            __syncthreads();                                // lastKeyOf is rewritten by the next round
+        }
+        // ---- weights of this chunk: destination words [w0, w1] of the macro block's bit range [chunkBit0, carryBits) ----
+        if (EMIT && carryBits > chunkBit0) {
+            const u32 skew = u32(tile.y & 31);              // the macro block's first bit within its first word
+            const u32 q0 = skew + chunkBit0, q1 = skew + carryBits;
+            const u32 w0 = q0 >> 5, w1 = (q1 - 1) >> 5;
+            u32* out = weights + (tile.y >> 5);
+            for (u32 w = w0 + t; w <= w1; w += T) {
+                const u32 a0 = max(q0, w << 5) - skew, b0 = min(q1, (w + 1) << 5) - skew;     // bits of the macro block in this word
+                u32 sg = 0;                                  // first segment whose bits end after a0
+                if (nChunk > 1) {
+                    u32 e = nChunk - 1;
+                    while (sg < e) {
+                        const u32 mid = (sg + e) >> 1;
+                        if (segBit1[mid] > a0) e = mid; else sg = mid + 1;
+                    }
+                }
+                u32 v = 0;
+                for (; sg < nChunk && segBit0[sg] < b0; ++sg) {
+                    if (max(a0, segBit0[sg]) >= min(b0, segBit1[sg])) continue;
+                    const ColorOpDev op = ops[lo + segBase + sg];
+                    if (op.kind == HDT_COLOR_OP_COPY) {
+#pragma unroll
+                        for (u32 half = 0; half < 2; ++half) {
+                            const u32 a = max(a0, half ? segMid[sg] : segBit0[sg]), b = min(b0, half ? segBit1[sg] : segMid[sg]);
+                            if (a < b) v |= read_stream_bits(oldLeaf, segDelta[half][sg] + a, b - a) >> ((a + skew) & 31);
+                        }
+                    } else {                                 // the stream of a repeated weight, from the phase this word starts in
+                        const u32 a = max(a0, segBit0[sg]), b = min(b0, segBit1[sg]);
+                        const u32 bpw = op.bitsPerWeight;
                         u64 pat = 0;
                         for (u32 k = 0; k < 64; k += bpw) pat |= (u64(op.weight) << (64 - bpw)) >> k;
-                        src.at = pat; src.period = bpw;
+                        v |= (u32((pat << ((a - segBit0[sg]) % bpw)) >> 32) & (0xFFFFFFFFu << (32 - (b - a)))) >> ((a + skew) & 31);
                     }
                 }
-            }
-            pieceKey[t] = key;
-            __syncthreads();
-            const u64 prevKey = t ? pieceKey[t - 1] : carryKey;
-            const bool starts = valid && (dstLocal == 0 || key != prevKey);   // ColorLeafBuilder::add, vwsc.h:606
-            const u32 bits = len * bpw;
-            u64 total;
-            const u64 excl = cta_exclusive_scan((u64(starts ? 1u : 0u) << 32) | bits, total);
-            const u32 nValid = min(T, totalPieces - pBase);
-            const u64 lastKey = pieceKey[nValid - 1];
-            if (EMIT && valid) {
-                const u32 bit = carryBits + u32(excl);     // weight bit offset relative to the macro block
-                if (starts) blocks[tile.x + carryBlocks + u32(excl >> 32)] = (u64(u32(key)) << 32) | make_block_header(bit, bpw, dstLocal);
-                if (bits) {
-                    const u32 q = bit + skew;
-                    if (((q + bits - 1) >> 5) - (q >> 5) + 1 > kLongPieceWords) {
-                        const u32 k = atomicAdd(&longCount, 1u);
-                        longQ[k] = q; longN[k] = bits; longAt[k] = src.at; longPeriod[k] = src.period;
-                    } else {
-                        write_bits(words, oldLeaf, src, q, bits, 0, 1);
-                    }
-                }
-            }
-            carryBlocks += u32(total >> 32);
-            carryBits += u32(total);
-            carryKey = lastKey;
-            __syncthreads();                                // pieceKey is rewritten by the next round; longCount is complete
-            if (EMIT) {
-                const u32 nLong = longCount;
-                for (u32 k = 0; k < nLong; ++k) write_bits(words, oldLeaf, BitSource{ longAt[k], longPeriod[k] }, longQ[k], longN[k], t, T);
-                __syncthreads();
-                if (t == 0) longCount = 0;
+                v = __byte_perm(v, 0, 0x0123);               // ColorUtils::swap_byte_order, build() :671-674
+                if (b0 - a0 == 32) out[w] = v;               // the word belongs to this chunk alone
+                else if (v) atomicOr(out + w, v);            // shared with the neighbouring chunk or macro block
             }
         }
         __syncthreads();                                    // the segment arrays are rewritten by the next chunk
     }
-    if (!EMIT) {
-        if (t == 0) tiles[blockIdx.x] = TilePair{ carryBlocks, carryBits };
-        return;
-    }
-    __syncthreads();
-    if (carryBits == 0) return;
-    const u32 nWords = (skew + carryBits + 31) >> 5;
-    u32* out = weights + (tile.y >> 5);
-    for (u32 k = t; k < nWords; k += T) {
-        const u32 v = __byte_perm(words[k], 0, 0x0123);   // ColorUtils::swap_byte_order, build() :671-674
-        if (k == 0 || k == nWords - 1) { if (v) atomicOr(out + k, v); }   // words shared with the neighbouring macro blocks
-        else out[k] = v;
-    }
+    if (!EMIT && t == 0) tiles[blockIdx.x] = TilePair{ carryBlocks, carryBits };
 }
 
 }  // namespace hdt
