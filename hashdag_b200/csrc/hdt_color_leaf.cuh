@@ -70,21 +70,26 @@ __device__ __forceinline__ V cta_exclusive_scan(V v, V& total)
     return base + inc - v;
 }
 
-// tiles[m] (counts) -> offsets[m] (exclusive prefix: first block index, weight bit offset); totals[0..1].
+// tiles[m] (counts) -> offsets[m] (exclusive prefix: first block index, weight bit offset); totals[0..1].  One CTA, a contiguous
+// run of tiles per thread.
 __global__ void __launch_bounds__(1024) scan_color_tiles_kernel(const TilePair* __restrict__ tiles, const u32 nTiles, ulonglong2* __restrict__ offsets,
                                                                  u64* __restrict__ totals)
 {
-    u64 carryBlocks = 0, carryBits = 0;
-    for (u32 base = 0; base < nTiles; base += blockDim.x) {
-        const u32 m = base + threadIdx.x;
-        const TilePair t = m < nTiles ? tiles[m] : TilePair{ 0, 0 };
-        u64 totB, totW;
-        const u64 eb = cta_exclusive_scan(u64(t.blocks), totB);
-        const u64 ew = cta_exclusive_scan(u64(t.bits), totW);
-        if (m < nTiles) offsets[m] = make_ulonglong2(carryBlocks + eb, carryBits + ew);
-        carryBlocks += totB; carryBits += totW;
+    const u32 per = (nTiles + blockDim.x - 1) / blockDim.x;
+    const u32 first = min(nTiles, threadIdx.x * per), end = min(nTiles, first + per);
+    u64 sumBlocks = 0, sumBits = 0;
+#pragma unroll 8
+    for (u32 m = first; m < end; ++m) { const TilePair t = tiles[m]; sumBlocks += t.blocks; sumBits += t.bits; }
+    u64 totB, totW;
+    u64 eb = cta_exclusive_scan(sumBlocks, totB);
+    u64 ew = cta_exclusive_scan(sumBits, totW);
+#pragma unroll 8
+    for (u32 m = first; m < end; ++m) {
+        const TilePair t = tiles[m];
+        offsets[m] = make_ulonglong2(eb, ew);
+        eb += t.blocks; ew += t.bits;
     }
-    if (threadIdx.x == 0) { totals[0] = carryBlocks; totals[1] = carryBits; }
+    if (threadIdx.x == 0) { totals[0] = totB; totals[1] = totW; }
 }
 
 // VariableColorsUtils::make_block_header, vwsc.h:32-52
@@ -128,47 +133,29 @@ __device__ __forceinline__ u32 find_block_warp(const ColorLeafDev& l, u32 macro,
     return lo + __popc(__ballot_sync(0xFFFFFFFFu, ok)) - 1;
 }
 
-// `take` (1..32) bits of the old leaf's weight stream from bit position `p`, left-aligned in the result.
-__device__ __forceinline__ u32 read_stream_bits(const ColorLeafDev& l, u64 p, u32 take)
+// A segment: the part of one op that lands in one macro block of the new leaf.  Written once by color_segments_kernel (the
+// searches in the old leaf are its dependent loads), read by the count and the emit pass.
+struct SegmentDev {
+    u32 dstLocal, len;          // first colour within the new macro block, colours
+    u32 nPieces;
+    u32 fill;                   // FILL: 1 | bitsPerWeight << 8 | weight << 16;  COPY: 0
+    u32 colorBits;              // FILL
+    u32 block0, last0;          // COPY: old block holding the first colour; last block of that block's macro block
+    u32 src0;                   // COPY: the first colour's index within its old macro block
+    u64 weightBase[2];          // COPY: weight bit offsets of that old macro block and of the one after it
+};
+static_assert(sizeof(SegmentDev) == 48, "three 16-byte loads");
+struct TileSegments { u32 first, count; };   // macro block of the new leaf -> its segments
+
+// The ops that reach into macro block m are ops[lo(m) .. last(m)]; their segments live in slots lo(m) + m + k (distinct for
+// every (m, k): lo(m + 1) >= last(m), so the slot ranges of consecutive macro blocks do not overlap).  One warp per macro block.
+__global__ void __launch_bounds__(256) color_segments_kernel(const ColorOpDev* __restrict__ ops, const u32 nOps, const ColorLeafDev oldLeaf, const u64 nColors,
+                                                              const u32 nTiles, SegmentDev* __restrict__ segs, TileSegments* __restrict__ tileSegs)
 {
-    const u64 wi = p >> 5;
-    const u32 sh = u32(p) & 31;
-    const u32 hi = wi < l.nWeights ? __byte_perm(__ldg(l.weights + wi), 0, 0x0123) : 0u;
-    const u32 lo = (sh + take > 32 && wi + 1 < l.nWeights) ? __byte_perm(__ldg(l.weights + wi + 1), 0, 0x0123) : 0u;
-    return __funnelshift_l(lo, hi, sh) & (0xFFFFFFFFu << (32 - take));
-}
-
-// One piece: what a thread keeps of it between the two halves of a round.
-struct Piece { u64 key; u32 dstLocal; u32 bits; };
-
-// One CTA per macro block of the new leaf.  EMIT = false: tiles[blockIdx] = {blocks started, weight bits}.  EMIT = true: the
-// macro block is written (offsets[blockIdx] = its first block index and weight bit offset; `weights` zeroed beforehand).
-//
-// The ops that reach into the macro block are taken T at a time (a "chunk" of segments, one per thread: where the segment's
-// colours come from, how many pieces it has), the pieces of a chunk T*K at a time (a "round": K consecutive pieces per thread,
-// one CTA-wide scan of {blocks started, weight bits}).  The weights are not moved piece by piece: the pieces of a COPY segment
-// are consecutive blocks of the old leaf, so the segment's weights are ONE contiguous bit range of the old stream, and a FILL
-// segment is a periodic pattern.  After the rounds of a chunk every destination word of the chunk's bit range is put together
-// by one thread from the segments that overlap it (funnel shifts) and stored once.
-template<bool EMIT>
-__global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const ColorOpDev* __restrict__ ops, const u32 nOps, const ColorLeafDev oldLeaf, const u64 nColors,
-                                                                      TilePair* __restrict__ tiles, const ulonglong2* __restrict__ offsets,
-                                                                      u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
-{
-    constexpr u32 T = kPieceThreads, K = kPiecesPerThread;
-    __shared__ u32 segPieceStart[T + 1];    // exclusive prefix of the pieces per segment
-    __shared__ u32 segDst[T], segLen[T], segBlock0[T], segLast0[T];
-    __shared__ u64 segSrc[T];
-    __shared__ u64 lastKeyOf[T];            // key of each thread's last piece of the round
-    // weight bits of the segments, relative to the macro block: bits [segBit0, segMid) come from the old stream at (bit + segDelta[0]),
-    // bits [segMid, segBit1) from (bit + segDelta[1]) -- a segment spans at most two macro blocks of the old leaf, and the stream of
-    // the old leaf need not be contiguous across them (the format lets a builder pad there)
-    __shared__ u32 segBit0[EMIT ? T : 1], segMid[EMIT ? T : 1], segBit1[EMIT ? T : 1];
-    __shared__ u64 segDelta[EMIT ? 2 : 1][EMIT ? T : 1];
-
-    const u32 t = threadIdx.x;
-    const u64 d0 = u64(blockIdx.x) * kColorsPerMacroBlock, d1 = min(d0 + kColorsPerMacroBlock, nColors);
-    // ops that reach into [d0, d1): lo = last op starting at or before d0, last = last op starting before d1
+    const u32 m = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+    if (m >= nTiles) return;
+    const u64 d0 = u64(m) * kColorsPerMacroBlock, d1 = min(d0 + kColorsPerMacroBlock, nColors);
+    // lo = last op starting at or before d0, last = last op starting before d1
     u32 lo = 0, hi = nOps - 1;
     while (lo < hi) {
         const u32 mid = (lo + hi + 1) >> 1;
@@ -181,8 +168,97 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
         if (__ldg(&ops[mid].dstStart) < d1) last = mid; else hi = mid - 1;
     }
     const u32 nSeg = last - lo + 1;
+    if (lane == 0) tileSegs[m] = TileSegments{ lo + m, nSeg };
     const u64 sharedOffset = oldLeaf.is_shared() ? oldLeaf.offset : 0;
+    const bool together = nSeg <= 4;            // a few segments: the warp searches each one with 32 probes at a time
+    for (u32 k = together ? 0 : lane; k < nSeg; k += together ? 1 : 32) {
+        const ColorOpDev op = ops[lo + k];
+        const u64 a = max(op.dstStart, d0), b = min(__ldg(&ops[lo + k + 1].dstStart), d1);
+        SegmentDev sg{};
+        sg.dstLocal = u32(a - d0); sg.len = u32(b - a);
+        sg.nPieces = 1;
+        if (op.kind == HDT_COLOR_OP_COPY) {
+            const u64 s0 = op.srcStart + (a - op.dstStart) + sharedOffset, s1 = s0 + (b - a) - 1;
+            const u32 m0 = u32(s0 / kColorsPerMacroBlock), m1 = u32(s1 / kColorsPerMacroBlock);
+            u32 last1, b1;
+            if (together) {
+                sg.block0 = find_block_warp(oldLeaf, m0, u32(s0 % kColorsPerMacroBlock), sg.last0);
+                b1 = find_block_warp(oldLeaf, m1, u32(s1 % kColorsPerMacroBlock), last1);
+            } else {
+                sg.block0 = find_block(oldLeaf, m0, u32(s0 % kColorsPerMacroBlock), sg.last0);
+                b1 = find_block(oldLeaf, m1, u32(s1 % kColorsPerMacroBlock), last1);
+            }
+            sg.nPieces = b1 - sg.block0 + 1;
+            sg.src0 = u32(s0 % kColorsPerMacroBlock);
+            sg.weightBase[0] = __ldg(oldLeaf.macroBlocks + 2 * u64(m0) + 1);
+            sg.weightBase[1] = m1 != m0 ? __ldg(oldLeaf.macroBlocks + 2 * u64(m1) + 1) : 0;
+        } else {
+            sg.fill = 1u | (op.bitsPerWeight << 8) | (op.weight << 16);
+            sg.colorBits = op.colorBits;
+        }
+        if (!together || lane == 0) segs[lo + m + k] = sg;
+    }
+}
 
+// `take` (1..32) bits of the old leaf's weight stream from bit position `p`, left-aligned in the result.
+__device__ __forceinline__ u32 read_stream_bits(const ColorLeafDev& l, u64 p, u32 take)
+{
+    const u64 wi = p >> 5;
+    const u32 sh = u32(p) & 31;
+    const u32 hi = wi < l.nWeights ? __byte_perm(__ldg(l.weights + wi), 0, 0x0123) : 0u;
+    const u32 lo = (sh + take > 32 && wi + 1 < l.nWeights) ? __byte_perm(__ldg(l.weights + wi + 1), 0, 0x0123) : 0u;
+    return __funnelshift_l(lo, hi, sh) & (0xFFFFFFFFu << (32 - take));
+}
+
+// Piece of a COPY segment that comes from block `b` of the old leaf (`blk`; `nextLocal` = first colour of block b + 1 within its
+// macro block).  Colour indices are relative to the old macro block of the segment's first colour: the segment is
+// [src0, src0 + len) there, at most 16384 long, so it ends before 2 * 16384.
+template<bool EMIT>
+__device__ __forceinline__ void copy_piece(const SegmentDev& sg, u32 b, u64 blk, u32 nextLocal, u32 j, u64& key, u32& dstLocal, u32& bits, u64& srcAt, u32& secondHalf)
+{
+    const u32 second = b > sg.last0 ? 1u : 0u;
+    const u32 hdr = u32(blk), startLocal = hdr & 0x3FFF;
+    const u32 base = second * u32(kColorsPerMacroBlock);
+    // starts increase inside a macro block: a smaller or equal one belongs to the next macro block
+    const u32 blockStart = base + startLocal, blockEnd = base + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
+    const u32 ps = max(blockStart, sg.src0), pe = min(blockEnd, sg.src0 + sg.len);
+    const u32 bpw = block_bits_per_weight(hdr);
+    key = (blk >> 32) | (u64(bpw) << 32);
+    dstLocal = sg.dstLocal + (ps - sg.src0);
+    bits = (pe - ps) * bpw;
+    if (EMIT) {
+        srcAt = (second ? sg.weightBase[1] : sg.weightBase[0]) + (hdr >> 16) + (ps - blockStart) * bpw;
+        if (second) secondHalf |= (b == sg.last0 + 1 ? 0x101u : 0x1u) << j;
+    }
+}
+
+// One CTA per macro block of the new leaf.  EMIT = false: tiles[blockIdx] = {blocks started, weight bits}.  EMIT = true: the
+// macro block is written (offsets[blockIdx] = its first block index and weight bit offset; `weights` zeroed beforehand).
+//
+// The segments of the macro block are taken T at a time (a "chunk", one per thread), the pieces of a chunk T*K at a time (a
+// "round": K consecutive pieces per thread, one CTA-wide scan of {blocks started, weight bits}).  The weights are not moved piece
+// by piece: the pieces of a COPY segment are consecutive blocks of the old leaf, so the segment's weights are one contiguous bit
+// range of the old stream per old macro block it touches (at most two), and a FILL segment is a periodic pattern.  After the
+// rounds of a chunk every destination word of the chunk's bit range is put together by one thread from the segments that
+// overlap it (funnel shifts) and stored once.
+template<bool EMIT>
+__global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const SegmentDev* __restrict__ segs, const TileSegments* __restrict__ tileSegs, const ColorLeafDev oldLeaf,
+                                                                      TilePair* __restrict__ tiles, const ulonglong2* __restrict__ offsets,
+                                                                      u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
+{
+    constexpr u32 T = kPieceThreads, K = kPiecesPerThread;
+    __shared__ SegmentDev seg[T];
+    __shared__ u32 segPieceStart[T + 1];    // exclusive prefix of the pieces per segment
+    __shared__ u64 lastKeyOf[T];            // key of each thread's last piece of the round
+    // weight bits of the segments, relative to the macro block: bits [segBit0, segMid) come from the old stream at (bit + segDelta[0]),
+    // bits [segMid, segBit1) from (bit + segDelta[1]) -- the stream of the old leaf need not be contiguous across its macro blocks
+    // (the format lets a builder pad there)
+    __shared__ u32 segBit0[EMIT ? T : 1], segMid[EMIT ? T : 1], segBit1[EMIT ? T : 1];
+    __shared__ u64 segDelta[EMIT ? 2 : 1][EMIT ? T : 1];
+
+    const u32 t = threadIdx.x;
+    const TileSegments mine = tileSegs[blockIdx.x];
+    const u32 nSeg = mine.count;
     ulonglong2 tile = make_ulonglong2(0, 0);
     if (EMIT) {
         tile = offsets[blockIdx.x];
@@ -198,39 +274,11 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
         const u32 nChunk = min(T, nSeg - segBase);
         const u32 chunkBit0 = carryBits;
         // ---- segments of this chunk ----
-        // (a few segments: one warp each, searching with 32 probes at a time; many: one thread each)
         u32 myPieces = 0;
-        const bool byWarp = nChunk <= T / 32;
-        const u32 mySeg = byWarp ? t / 32 : t;
-        if (mySeg < nChunk) {
-            const ColorOpDev op = ops[lo + segBase + mySeg];
-            const u64 a = max(op.dstStart, d0), b = min(__ldg(&ops[lo + segBase + mySeg + 1].dstStart), d1);
-            u64 s0 = 0;
-            u32 b0 = 0, last0 = 0;
-            myPieces = 1;
-            if (op.kind == HDT_COLOR_OP_COPY) {
-                s0 = op.srcStart + (a - op.dstStart) + sharedOffset;
-                const u64 s1 = s0 + (b - a) - 1;
-                u32 last1, b1;
-                if (byWarp) {
-                    b0 = find_block_warp(oldLeaf, u32(s0 / kColorsPerMacroBlock), u32(s0 % kColorsPerMacroBlock), last0);
-                    b1 = find_block_warp(oldLeaf, u32(s1 / kColorsPerMacroBlock), u32(s1 % kColorsPerMacroBlock), last1);
-                } else {
-                    b0 = find_block(oldLeaf, u32(s0 / kColorsPerMacroBlock), u32(s0 % kColorsPerMacroBlock), last0);
-                    b1 = find_block(oldLeaf, u32(s1 / kColorsPerMacroBlock), u32(s1 % kColorsPerMacroBlock), last1);
-                }
-                myPieces = b1 - b0 + 1;
-            }
-            if (!byWarp || (t & 31) == 0) {
-                segDst[mySeg] = u32(a - d0); segLen[mySeg] = u32(b - a);
-                segSrc[mySeg] = s0; segBlock0[mySeg] = b0; segLast0[mySeg] = last0;
-                if (byWarp) segPieceStart[mySeg] = myPieces;   // handed to thread mySeg for the scan below
-            }
-        }
-        if (byWarp) {
-            __syncthreads();
-            myPieces = t < nChunk ? segPieceStart[t] : 0;
-            __syncthreads();
+        if (t < nChunk) {
+            const SegmentDev sg = segs[mine.first + segBase + t];
+            seg[t] = sg;
+            myPieces = sg.nPieces;
         }
         u32 totalPieces;
         const u32 myStart = cta_exclusive_scan(myPieces, totalPieces);
@@ -240,54 +288,70 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
         // ---- pieces of this chunk, T * K at a time ----
         for (u32 pBase = 0; pBase < totalPieces; pBase += T * K) {
             const u32 p0 = pBase + t * K;
-            u32 s = 0;                           // segment of piece p0: last one starting at or before it
-            if (nChunk > 1 && p0 < totalPieces) {
+            const u32 nMine = p0 >= totalPieces ? 0u : min(K, totalPieces - p0);
+            u32 s0idx = 0;                       // segment of piece p0: last one starting at or before it
+            if (nChunk > 1 && nMine) {
                 u32 e = nChunk - 1;
-                while (s < e) {
-                    const u32 mid = (s + e + 1) >> 1;
-                    if (segPieceStart[mid] <= p0) s = mid; else e = mid - 1;
+                while (s0idx < e) {
+                    const u32 mid = (s0idx + e + 1) >> 1;
+                    if (segPieceStart[mid] <= p0) s0idx = mid; else e = mid - 1;
                 }
             }
-            Piece pc[K];
+            u64 key[K];
+            u32 dstLocal[K], bits[K];
             u64 srcAt[EMIT ? K : 1];
-            u32 myBits = 0, secondHalf = 0;      // bit j: piece j lies in the second old macro block of its segment
+            u32 myBits = 0, secondHalf = 0;      // bit j: piece j lies in the second old macro block of its segment; bit 8 + j: the first such piece
 #pragma unroll
             for (u32 j = 0; j < K; ++j) {
-                const u32 p = p0 + j;
-                pc[j].key = 0; pc[j].dstLocal = 0; pc[j].bits = 0;
+                key[j] = 0; dstLocal[j] = 0; bits[j] = 0;
                 if (EMIT) srcAt[j] = 0;
-                if (p < totalPieces) {
-                    while (p >= segPieceStart[s + 1]) ++s;
-                    const ColorOpDev op = ops[lo + segBase + s];
-                    if (op.kind == HDT_COLOR_OP_COPY) {
-                        const u32 b = segBlock0[s] + (p - segPieceStart[s]);
-                        const u64 s0 = segSrc[s], s1 = s0 + segLen[s];
-                        const u64 macroBase = (s0 / kColorsPerMacroBlock + (b > segLast0[s] ? 1 : 0)) * kColorsPerMacroBlock;   // a segment spans at most two old macro blocks
-                        const u64 blk = __ldg(oldLeaf.blocks + b);
-                        const u32 hdr = u32(blk), startLocal = hdr & 0x3FFF;
-                        const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
-                        // starts increase inside a macro block: a smaller or equal one belongs to the next macro block
-                        const u64 blockStart = macroBase + startLocal, blockEnd = macroBase + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
-                        const u64 ps = max(blockStart, s0), pe = min(blockEnd, s1);
-                        const u32 bpw = block_bits_per_weight(hdr);
-                        pc[j].key = (blk >> 32) | (u64(bpw) << 32);
-                        pc[j].dstLocal = segDst[s] + u32(ps - s0);
-                        pc[j].bits = u32(pe - ps) * bpw;
-                        if (EMIT && bpw) srcAt[j] = __ldg(oldLeaf.macroBlocks + 2 * (macroBase / kColorsPerMacroBlock) + 1) + (hdr >> 16) + (ps - blockStart) * bpw;
-                        if (EMIT && b > segLast0[s]) secondHalf |= (b == segLast0[s] + 1 ? 0x101u : 0x1u) << j;   // (bit 8 + j: the first such piece)
-                    } else {
-                        pc[j].key = u64(op.colorBits) | (u64(op.bitsPerWeight) << 32);
-                        pc[j].dstLocal = segDst[s];
-                        pc[j].bits = segLen[s] * op.bitsPerWeight;
+            }
+            const bool oneCopy = nChunk == 1 && !seg[0].fill;
+            if (oneCopy) {
+                // the usual case, one COPY segment: the thread's pieces are K consecutive blocks of the old leaf (+ the start of the next)
+                const SegmentDev sg = seg[0];
+                const u32 b = sg.block0 + p0;
+                u64 blk[K + 1];
+#pragma unroll
+                for (u32 j = 0; j <= K; ++j) blk[j] = (j <= nMine && u64(b) + j < oldLeaf.nBlocks) ? __ldg(oldLeaf.blocks + b + j) : 0;
+#pragma unroll
+                for (u32 j = 0; j < K; ++j) {
+                    if (j < nMine) {
+                        copy_piece<EMIT>(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, j, key[j], dstLocal[j], bits[j], srcAt[EMIT ? j : 0], secondHalf);
+                        myBits += bits[j];
                     }
-                    myBits += pc[j].bits;
+                }
+            } else {
+                u32 s = s0idx, segEnd = 0;       // pieces below segEnd belong to segment s, whose fields are in sg / pieceStart
+                SegmentDev sg{};
+                u32 pieceStart = 0;
+#pragma unroll
+                for (u32 j = 0; j < K; ++j) {
+                    if (j < nMine) {
+                        const u32 p = p0 + j;
+                        if (p >= segEnd) {
+                            if (segEnd) ++s;
+                            while (p >= segPieceStart[s + 1]) ++s;
+                            sg = seg[s]; pieceStart = segPieceStart[s]; segEnd = segPieceStart[s + 1];
+                        }
+                        if (!sg.fill) {
+                            const u32 b = sg.block0 + (p - pieceStart);
+                            const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
+                            copy_piece<EMIT>(sg, b, __ldg(oldLeaf.blocks + b), nextLocal, j, key[j], dstLocal[j], bits[j], srcAt[EMIT ? j : 0], secondHalf);
+                        } else {
+                            const u32 bpw = (sg.fill >> 8) & 0xFF;
+                            key[j] = u64(sg.colorBits) | (u64(bpw) << 32);
+                            dstLocal[j] = sg.dstLocal;
+                            bits[j] = sg.len * bpw;
+                        }
+                        myBits += bits[j];
+                    }
                 }
             }
-            const u32 nMine = p0 >= totalPieces ? 0u : min(K, totalPieces - p0);
             if (nMine) {
-                u64 k = pc[0].key;
+                u64 k = key[0];
 #pragma unroll
-                for (u32 j = 1; j < K; ++j) if (j < nMine) k = pc[j].key;
+                for (u32 j = 1; j < K; ++j) if (j < nMine) k = key[j];
                 lastKeyOf[t] = k;
             }
             __syncthreads();
@@ -295,8 +359,8 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
             u32 startsMask = 0;
 #pragma unroll
             for (u32 j = 0; j < K; ++j) {
-                if (j < nMine && (pc[j].dstLocal == 0 || pc[j].key != prevKey)) startsMask |= 1u << j;   // ColorLeafBuilder::add, vwsc.h:606
-                prevKey = pc[j].key;
+                if (j < nMine && (dstLocal[j] == 0 || key[j] != prevKey)) startsMask |= 1u << j;   // ColorLeafBuilder::add, vwsc.h:606
+                prevKey = key[j];
             }
             // {blocks started, weight bits} in one word: a macro block has at most 65536 bits, a round at most T * K pieces
             static_assert(T * K < 4096, "12 bits for the blocks a round starts");
@@ -307,27 +371,24 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
             if (EMIT && nMine) {
                 u64 blockIndex = tile.x + carryBlocks + (excl >> 20);
                 u32 bit = carryBits + (excl & 0xFFFFF);     // weight bit offset relative to the macro block
-                s = 0;
-                if (nChunk > 1) {
-                    u32 e = nChunk - 1;
-                    while (s < e) {
-                        const u32 mid = (s + e + 1) >> 1;
-                        if (segPieceStart[mid] <= p0) s = mid; else e = mid - 1;
-                    }
-                }
+                u32 s = s0idx, segEnd = nChunk == 1 ? totalPieces : 0, pieceStart = 0;
 #pragma unroll
                 for (u32 j = 0; j < K; ++j) {
                     if (j < nMine) {
                         const u32 p = p0 + j;
-                        while (p >= segPieceStart[s + 1]) ++s;
-                        const u32 bpw = u32(pc[j].key >> 32);
-                        if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(u32(pc[j].key)) << 32) | make_block_header(bit, bpw, pc[j].dstLocal);
+                        if (p >= segEnd) {
+                            if (segEnd) ++s;
+                            while (p >= segPieceStart[s + 1]) ++s;
+                            pieceStart = segPieceStart[s]; segEnd = segPieceStart[s + 1];
+                        }
+                        const u32 bpw = u32(key[j] >> 32);
+                        if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(u32(key[j])) << 32) | make_block_header(bit, bpw, dstLocal[j]);
                         const u32 half = (secondHalf >> j) & 1;
-                        if (p == segPieceStart[s]) segBit0[s] = bit;
+                        if (p == pieceStart) segBit0[s] = bit;
                         if (secondHalf & (0x100u << j)) segMid[s] = bit;
-                        if (pc[j].bits) segDelta[half][s] = srcAt[j] - bit;           // the same for every piece of the half (FILL: unused)
-                        bit += pc[j].bits;
-                        if (p + 1 == segPieceStart[s + 1]) {
+                        if (bits[j]) segDelta[half][s] = srcAt[j] - bit;              // the same for every piece of the half (FILL: unused)
+                        bit += bits[j];
+                        if (p + 1 == segEnd) {
                             segBit1[s] = bit;
                             if (!half) segMid[s] = bit;                               // no second half
                         }
@@ -347,30 +408,42 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Color
             u32* out = weights + (tile.y >> 5);
             for (u32 w = w0 + t; w <= w1; w += T) {
                 const u32 a0 = max(q0, w << 5) - skew, b0 = min(q1, (w + 1) << 5) - skew;     // bits of the macro block in this word
-                u32 sg = 0;                                  // first segment whose bits end after a0
+                u32 sgi = 0;                                 // first segment whose bits end after a0
                 if (nChunk > 1) {
                     u32 e = nChunk - 1;
-                    while (sg < e) {
-                        const u32 mid = (sg + e) >> 1;
-                        if (segBit1[mid] > a0) e = mid; else sg = mid + 1;
+                    while (sgi < e) {
+                        const u32 mid = (sgi + e) >> 1;
+                        if (segBit1[mid] > a0) e = mid; else sgi = mid + 1;
                     }
                 }
                 u32 v = 0;
-                for (; sg < nChunk && segBit0[sg] < b0; ++sg) {
-                    if (max(a0, segBit0[sg]) >= min(b0, segBit1[sg])) continue;
-                    const ColorOpDev op = ops[lo + segBase + sg];
-                    if (op.kind == HDT_COLOR_OP_COPY) {
+                if (b0 - a0 == 32 && !seg[sgi].fill) {       // the usual case: a whole word from one old macro block of one COPY segment
+                    const u32 mid = segMid[sgi];
+                    const bool in0 = a0 >= segBit0[sgi] && b0 <= mid, in1 = a0 >= mid && b0 <= segBit1[sgi];
+                    const u64 p = segDelta[in1 ? 1 : 0][sgi] + a0;
+                    if ((in0 || in1) && (p >> 5) + 1 < oldLeaf.nWeights) {
+                        const u32 sh = u32(p) & 31;
+                        const u32* src = oldLeaf.weights + (p >> 5);
+                        const u32 hi = __byte_perm(__ldg(src), 0, 0x0123), lo = sh ? __byte_perm(__ldg(src + 1), 0, 0x0123) : 0u;
+                        out[w] = __byte_perm(__funnelshift_l(lo, hi, sh), 0, 0x0123);
+                        continue;
+                    }
+                }
+                for (; sgi < nChunk && segBit0[sgi] < b0; ++sgi) {
+                    if (max(a0, segBit0[sgi]) >= min(b0, segBit1[sgi])) continue;
+                    const u32 fill = seg[sgi].fill;
+                    if (!fill) {
 #pragma unroll
                         for (u32 half = 0; half < 2; ++half) {
-                            const u32 a = max(a0, half ? segMid[sg] : segBit0[sg]), b = min(b0, half ? segBit1[sg] : segMid[sg]);
-                            if (a < b) v |= read_stream_bits(oldLeaf, segDelta[half][sg] + a, b - a) >> ((a + skew) & 31);
+                            const u32 a = max(a0, half ? segMid[sgi] : segBit0[sgi]), b = min(b0, half ? segBit1[sgi] : segMid[sgi]);
+                            if (a < b) v |= read_stream_bits(oldLeaf, segDelta[half][sgi] + a, b - a) >> ((a + skew) & 31);
                         }
                     } else {                                 // the stream of a repeated weight, from the phase this word starts in
-                        const u32 a = max(a0, segBit0[sg]), b = min(b0, segBit1[sg]);
-                        const u32 bpw = op.bitsPerWeight;
+                        const u32 a = max(a0, segBit0[sgi]), b = min(b0, segBit1[sgi]);
+                        const u32 bpw = (fill >> 8) & 0xFF;
                         u64 pat = 0;
-                        for (u32 k = 0; k < 64; k += bpw) pat |= (u64(op.weight) << (64 - bpw)) >> k;
-                        v |= (u32((pat << ((a - segBit0[sg]) % bpw)) >> 32) & (0xFFFFFFFFu << (32 - (b - a)))) >> ((a + skew) & 31);
+                        for (u32 k = 0; k < 64; k += bpw) pat |= (u64(fill >> 16) << (64 - bpw)) >> k;
+                        v |= (u32((pat << ((a - segBit0[sgi]) % bpw)) >> 32) & (0xFFFFFFFFu << (32 - (b - a)))) >> ((a + skew) & 31);
                     }
                 }
                 v = __byte_perm(v, 0, 0x0123);               // ColorUtils::swap_byte_order, build() :671-674

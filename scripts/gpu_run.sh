@@ -7,6 +7,7 @@
 #   launches                  ncu launch list of a short bench run (per-launch device times, cold caches)
 #   ncu                       ncu --set full of the three per-pixel kernels of a short bench run
 #   smoke                     __graft_entry__.smoke()
+#   colorleaf                 colour-leaf rebuild: its tests, scripts/bench_color_leaf.py, ncu --set full of its kernels
 #   golden <generator.py>     a tests/golden/make_*.py fixture generator (reference harness) -> gpurun_out/golden/
 set -x
 cd "$(dirname "$0")/.."
@@ -29,6 +30,12 @@ ncu)
     ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_raw.csv 2>/dev/null ;;
 smoke)
     python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/${TAG}_smoke.log ;;
+colorleaf)
+    timeout 900 python -m pytest tests/test_gpu_color_leaf.py -x -q 2>&1 | tail -30 | tee gpurun_out/${TAG}_cl_pytest.log
+    timeout 600 python scripts/bench_color_leaf.py > gpurun_out/${TAG}_color_leaf_bench.json 2> gpurun_out/${TAG}_color_leaf_bench.err
+    tail -c 1500 gpurun_out/${TAG}_color_leaf_bench.json
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:color_ -c 4 -f -o gpurun_out/${TAG}_cl_prof python scripts/bench_color_leaf.py --reps 1 > gpurun_out/${TAG}_cl_ncu.log 2>&1
+    ncu -i gpurun_out/${TAG}_cl_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_cl_prof_raw.csv 2>/dev/null ;;
 golden)
     timeout 900 python "$1" gpurun_out/golden 2>&1 | tail -20 | tee gpurun_out/${TAG}_golden.log ;;
 *)
