@@ -32,7 +32,7 @@
 namespace hdt {
 
 constexpr u32 kPieceThreads = 256;
-constexpr u32 kPiecesPerThread = 4;
+constexpr u32 kPiecesPerThread = 6;
 
 // hdt_color_op with the exclusive prefix of the counts (where the op's first colour lands in the new leaf).
 struct ColorOpDev { u64 dstStart; u64 srcStart; u32 kind; u32 bitsPerWeight; u32 colorBits; u32 weight; };
@@ -70,26 +70,33 @@ __device__ __forceinline__ V cta_exclusive_scan(V v, V& total)
     return base + inc - v;
 }
 
-// tiles[m] (counts) -> offsets[m] (exclusive prefix: first block index, weight bit offset); totals[0..1].  One CTA, a contiguous
-// run of tiles per thread.
-__global__ void __launch_bounds__(1024) scan_color_tiles_kernel(const TilePair* __restrict__ tiles, const u32 nTiles, ulonglong2* __restrict__ offsets,
-                                                                 u64* __restrict__ totals)
+// tiles[m] (counts) -> offsets[m] (exclusive prefix: first block index, weight bit offset; offsets[nTiles] = the totals) and
+// totals[0..1].  The count pass has added every tile's pair to groupSums[m / 256] (blocks << 32 | bits: a leaf has fewer than
+// 2^30 blocks and 2^32 bits); one CTA per group of 256 tiles adds the groups in front of it and scans its own tiles.
+// The weight words two macro blocks share (the word a macro block's first bit falls into) are put together with atomicOr by
+// the emit pass: they are zeroed here, if the caller's buffer reaches that far.
+constexpr u32 kTileGroup = 256;
+__global__ void __launch_bounds__(kTileGroup) scan_color_tiles_kernel(const TilePair* __restrict__ tiles, const u32 nTiles, const u64* __restrict__ groupSums,
+                                                                       ulonglong2* __restrict__ offsets, u64* __restrict__ totals, u32* __restrict__ weights, const u64 weightsCapacity)
 {
-    const u32 per = (nTiles + blockDim.x - 1) / blockDim.x;
-    const u32 first = min(nTiles, threadIdx.x * per), end = min(nTiles, first + per);
-    u64 sumBlocks = 0, sumBits = 0;
-#pragma unroll 8
-    for (u32 m = first; m < end; ++m) { const TilePair t = tiles[m]; sumBlocks += t.blocks; sumBits += t.bits; }
-    u64 totB, totW;
-    u64 eb = cta_exclusive_scan(sumBlocks, totB);
-    u64 ew = cta_exclusive_scan(sumBits, totW);
-#pragma unroll 8
-    for (u32 m = first; m < end; ++m) {
-        const TilePair t = tiles[m];
-        offsets[m] = make_ulonglong2(eb, ew);
-        eb += t.blocks; ew += t.bits;
+    const u32 t = threadIdx.x, g = blockIdx.x, m = g * kTileGroup + t;
+    const TilePair mine = m < nTiles ? tiles[m] : TilePair{ 0, 0 };
+    u64 front = t < g ? groupSums[t] : 0;            // at most 65536 / 256 = 256 groups
+    u64 base;
+    cta_exclusive_scan(front, base);                 // (only the total is used)
+    u64 total;
+    const u64 at = base + cta_exclusive_scan((u64(mine.blocks) << 32) | mine.bits, total);
+    if (m < nTiles) {
+        offsets[m] = make_ulonglong2(at >> 32, at & 0xFFFFFFFFull);
+        const u64 word = (at & 0xFFFFFFFFull) >> 5;
+        if (weights && word < weightsCapacity) weights[word] = 0;
     }
-    if (threadIdx.x == 0) { totals[0] = totB; totals[1] = totW; }
+    if (m + 1 == nTiles) {
+        const u64 end = at + ((u64(mine.blocks) << 32) | mine.bits);
+        totals[0] = end >> 32; totals[1] = end & 0xFFFFFFFFull;
+        offsets[nTiles] = make_ulonglong2(end >> 32, end & 0xFFFFFFFFull);
+        if (weights && ((end & 0xFFFFFFFFull) >> 5) < weightsCapacity) weights[(end & 0xFFFFFFFFull) >> 5] = 0;
+    }
 }
 
 // VariableColorsUtils::make_block_header, vwsc.h:32-52
@@ -210,11 +217,19 @@ __device__ __forceinline__ u32 read_stream_bits(const ColorLeafDev& l, u64 p, u3
     return __funnelshift_l(lo, hi, sh) & (0xFFFFFFFFu << (32 - take));
 }
 
+// A piece as a thread keeps it between the two halves of a round: colorBits, and
+// first colour within the new macro block (14 bits) | bitsPerWeight << 14 | colours << 17.
+__device__ __forceinline__ u32 pack_piece(u32 dstLocal, u32 bpw, u32 len) { return dstLocal | (bpw << 14) | (len << 17); }
+__device__ __forceinline__ u32 piece_dst(u32 pk) { return pk & 0x3FFF; }
+__device__ __forceinline__ u32 piece_bpw(u32 pk) { return (pk >> 14) & 7; }
+__device__ __forceinline__ u32 piece_bits(u32 pk) { return (pk >> 17) * piece_bpw(pk); }
+__device__ __forceinline__ u64 piece_key(u32 colorBits, u32 pk) { return u64(colorBits) | (u64(piece_bpw(pk)) << 32); }   // equal keys continue a block
+
 // Piece of a COPY segment that comes from block `b` of the old leaf (`blk`; `nextLocal` = first colour of block b + 1 within its
 // macro block).  Colour indices are relative to the old macro block of the segment's first colour: the segment is
-// [src0, src0 + len) there, at most 16384 long, so it ends before 2 * 16384.
-template<bool EMIT>
-__device__ __forceinline__ void copy_piece(const SegmentDev& sg, u32 b, u64 blk, u32 nextLocal, u32 j, u64& key, u32& dstLocal, u32& bits, u64& srcAt, u32& secondHalf)
+// [src0, src0 + len) there, at most 16384 long, so it ends before 2 * 16384.  -> packed piece; srcAt = where its first weight
+// bit sits in the old stream.
+__device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, u32 nextLocal, u64& srcAt)
 {
     const u32 second = b > sg.last0 ? 1u : 0u;
     const u32 hdr = u32(blk), startLocal = hdr & 0x3FFF;
@@ -223,13 +238,8 @@ __device__ __forceinline__ void copy_piece(const SegmentDev& sg, u32 b, u64 blk,
     const u32 blockStart = base + startLocal, blockEnd = base + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
     const u32 ps = max(blockStart, sg.src0), pe = min(blockEnd, sg.src0 + sg.len);
     const u32 bpw = block_bits_per_weight(hdr);
-    key = (blk >> 32) | (u64(bpw) << 32);
-    dstLocal = sg.dstLocal + (ps - sg.src0);
-    bits = (pe - ps) * bpw;
-    if (EMIT) {
-        srcAt = (second ? sg.weightBase[1] : sg.weightBase[0]) + (hdr >> 16) + (ps - blockStart) * bpw;
-        if (second) secondHalf |= (b == sg.last0 + 1 ? 0x101u : 0x1u) << j;
-    }
+    srcAt = (second ? sg.weightBase[1] : sg.weightBase[0]) + (hdr >> 16) + (ps - blockStart) * bpw;
+    return pack_piece(sg.dstLocal + (ps - sg.src0), bpw, pe - ps);
 }
 
 // One CTA per macro block of the new leaf.  EMIT = false: tiles[blockIdx] = {blocks started, weight bits}.  EMIT = true: the
@@ -243,7 +253,7 @@ __device__ __forceinline__ void copy_piece(const SegmentDev& sg, u32 b, u64 blk,
 // overlap it (funnel shifts) and stored once.
 template<bool EMIT>
 __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const SegmentDev* __restrict__ segs, const TileSegments* __restrict__ tileSegs, const ColorLeafDev oldLeaf,
-                                                                      TilePair* __restrict__ tiles, const ulonglong2* __restrict__ offsets,
+                                                                      TilePair* __restrict__ tiles, u64* __restrict__ groupSums, const ulonglong2* __restrict__ offsets,
                                                                       u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
 {
     constexpr u32 T = kPieceThreads, K = kPiecesPerThread;
@@ -269,6 +279,13 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
     }
     u32 carryBlocks = 0, carryBits = 0;          // blocks started / weight bits of this macro block so far (CTA-uniform)
     u64 carryKey = 0;                            // key of the last piece so far
+    if (EMIT && nSeg > T) {
+        // several chunks: the words two chunks share are put together with atomicOr as well.  Zero the macro block's words,
+        // except the first and the last (shared with the neighbours, zeroed by the scan)
+        const u64 endBit = offsets[blockIdx.x + 1].y;
+        for (u64 w = (tile.y >> 5) + 1 + t; w + 1 <= (endBit >> 5); w += T) weights[w] = 0;
+        __syncthreads();
+    }
 
     for (u32 segBase = 0; segBase < nSeg; segBase += T) {
         const u32 nChunk = min(T, nSeg - segBase);
@@ -285,6 +302,7 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
         if (t < nChunk) segPieceStart[t] = myStart;
         if (t == 0) segPieceStart[nChunk] = totalPieces;
         __syncthreads();
+        const bool oneCopy = nChunk == 1 && !seg[0].fill;   // the usual case: the macro block is one COPY segment
         // ---- pieces of this chunk, T * K at a time ----
         for (u32 pBase = 0; pBase < totalPieces; pBase += T * K) {
             const u32 p0 = pBase + t * K;
@@ -297,28 +315,34 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
                     if (segPieceStart[mid] <= p0) s0idx = mid; else e = mid - 1;
                 }
             }
-            u64 key[K];
-            u32 dstLocal[K], bits[K];
-            u64 srcAt[EMIT ? K : 1];
-            u32 myBits = 0, secondHalf = 0;      // bit j: piece j lies in the second old macro block of its segment; bit 8 + j: the first such piece
+            u32 cb[K], pk[K];                    // the thread's pieces: colorBits, pack_piece()
+            u32 myBits = 0;
+            // oneCopy, EMIT: where the old stream continues for the thread's first weighted piece of each half of the segment
+            // (position of that piece's first bit minus the thread's bits in front of it), and which halves it has
+            u64 at0 = 0, at1 = 0;
+            u32 haveAt = 0;
 #pragma unroll
-            for (u32 j = 0; j < K; ++j) {
-                key[j] = 0; dstLocal[j] = 0; bits[j] = 0;
-                if (EMIT) srcAt[j] = 0;
-            }
-            const bool oneCopy = nChunk == 1 && !seg[0].fill;
+            for (u32 j = 0; j < K; ++j) { cb[j] = 0; pk[j] = 0; }
             if (oneCopy) {
-                // the usual case, one COPY segment: the thread's pieces are K consecutive blocks of the old leaf (+ the start of the next)
+                // the thread's pieces are K consecutive blocks of the old leaf (+ the start of the one after them)
                 const SegmentDev sg = seg[0];
                 const u32 b = sg.block0 + p0;
                 u64 blk[K + 1];
 #pragma unroll
-                for (u32 j = 0; j <= K; ++j) blk[j] = (j <= nMine && u64(b) + j < oldLeaf.nBlocks) ? __ldg(oldLeaf.blocks + b + j) : 0;
+                const u32 nLoad = u32(min(u64(nMine) + 1, oldLeaf.nBlocks - b));   // (b < nBlocks: the thread has pieces)
+                for (u32 j = 0; j <= K; ++j) blk[j] = j < nLoad ? __ldg(oldLeaf.blocks + b + j) : 0;
 #pragma unroll
                 for (u32 j = 0; j < K; ++j) {
                     if (j < nMine) {
-                        copy_piece<EMIT>(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, j, key[j], dstLocal[j], bits[j], srcAt[EMIT ? j : 0], secondHalf);
-                        myBits += bits[j];
+                        u64 srcAt;
+                        pk[j] = copy_piece(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, srcAt);
+                        cb[j] = u32(blk[j] >> 32);
+                        const u32 bits = piece_bits(pk[j]), half = b + j > sg.last0 ? 1u : 0u;
+                        if (EMIT && bits && !(haveAt & (1u << half))) {
+                            if (half) at1 = srcAt - myBits; else at0 = srcAt - myBits;
+                            haveAt |= 1u << half;
+                        }
+                        myBits += bits;
                     }
                 }
             } else {
@@ -336,31 +360,34 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
                         }
                         if (!sg.fill) {
                             const u32 b = sg.block0 + (p - pieceStart);
+                            const u64 blk = __ldg(oldLeaf.blocks + b);
                             const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
-                            copy_piece<EMIT>(sg, b, __ldg(oldLeaf.blocks + b), nextLocal, j, key[j], dstLocal[j], bits[j], srcAt[EMIT ? j : 0], secondHalf);
+                            u64 srcAt;
+                            pk[j] = copy_piece(sg, b, blk, nextLocal, srcAt);
+                            cb[j] = u32(blk >> 32);
                         } else {
-                            const u32 bpw = (sg.fill >> 8) & 0xFF;
-                            key[j] = u64(sg.colorBits) | (u64(bpw) << 32);
-                            dstLocal[j] = sg.dstLocal;
-                            bits[j] = sg.len * bpw;
+                            pk[j] = pack_piece(sg.dstLocal, (sg.fill >> 8) & 0xFF, sg.len);
+                            cb[j] = sg.colorBits;
                         }
-                        myBits += bits[j];
+                        myBits += piece_bits(pk[j]);
                     }
                 }
             }
             if (nMine) {
-                u64 k = key[0];
+                u32 lastCb = cb[0], lastPk = pk[0];
 #pragma unroll
-                for (u32 j = 1; j < K; ++j) if (j < nMine) k = key[j];
-                lastKeyOf[t] = k;
+                for (u32 j = 1; j < K; ++j) if (j < nMine) { lastCb = cb[j]; lastPk = pk[j]; }
+                lastKeyOf[t] = piece_key(lastCb, lastPk);
             }
             __syncthreads();
-            u64 prevKey = t ? lastKeyOf[t - 1] : carryKey;      // (threads in front of a thread that has pieces have K each)
+            const u64 prevKey = t ? lastKeyOf[t - 1] : carryKey;      // (threads in front of a thread that has pieces have K each)
+            u32 prevCb = u32(prevKey), prevBpw = u32(prevKey >> 32);
             u32 startsMask = 0;
 #pragma unroll
             for (u32 j = 0; j < K; ++j) {
-                if (j < nMine && (dstLocal[j] == 0 || key[j] != prevKey)) startsMask |= 1u << j;   // ColorLeafBuilder::add, vwsc.h:606
-                prevKey = key[j];
+                const u32 bpw = piece_bpw(pk[j]);
+                if (j < nMine && (piece_dst(pk[j]) == 0 || cb[j] != prevCb || bpw != prevBpw)) startsMask |= 1u << j;   // ColorLeafBuilder::add, vwsc.h:606
+                prevCb = cb[j]; prevBpw = bpw;
             }
             // {blocks started, weight bits} in one word: a macro block has at most 65536 bits, a round at most T * K pieces
             static_assert(T * K < 4096, "12 bits for the blocks a round starts");
@@ -371,26 +398,56 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
             if (EMIT && nMine) {
                 u64 blockIndex = tile.x + carryBlocks + (excl >> 20);
                 u32 bit = carryBits + (excl & 0xFFFFF);     // weight bit offset relative to the macro block
-                u32 s = s0idx, segEnd = nChunk == 1 ? totalPieces : 0, pieceStart = 0;
+                if (oneCopy) {
+                    const u32 b = seg[0].block0 + p0, last0 = seg[0].last0;
+                    if (haveAt & 1) segDelta[0][0] = at0 - bit;                       // the same from every thread that has one
+                    if (haveAt & 2) segDelta[1][0] = at1 - bit;
+                    if (p0 == 0) segBit0[0] = bit;
 #pragma unroll
-                for (u32 j = 0; j < K; ++j) {
-                    if (j < nMine) {
-                        const u32 p = p0 + j;
-                        if (p >= segEnd) {
-                            if (segEnd) ++s;
-                            while (p >= segPieceStart[s + 1]) ++s;
-                            pieceStart = segPieceStart[s]; segEnd = segPieceStart[s + 1];
+                    for (u32 j = 0; j < K; ++j) {
+                        if (j < nMine) {
+                            if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(cb[j]) << 32) | make_block_header(bit, piece_bpw(pk[j]), piece_dst(pk[j]));
+                            if (b + j == last0 + 1) segMid[0] = bit;                  // the first piece from the second old macro block
+                            bit += piece_bits(pk[j]);
                         }
-                        const u32 bpw = u32(key[j] >> 32);
-                        if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(u32(key[j])) << 32) | make_block_header(bit, bpw, dstLocal[j]);
-                        const u32 half = (secondHalf >> j) & 1;
-                        if (p == pieceStart) segBit0[s] = bit;
-                        if (secondHalf & (0x100u << j)) segMid[s] = bit;
-                        if (bits[j]) segDelta[half][s] = srcAt[j] - bit;              // the same for every piece of the half (FILL: unused)
-                        bit += bits[j];
-                        if (p + 1 == segEnd) {
-                            segBit1[s] = bit;
-                            if (!half) segMid[s] = bit;                               // no second half
+                    }
+                    if (p0 + nMine == totalPieces) {
+                        segBit1[0] = bit;
+                        if (b + nMine - 1 <= last0) segMid[0] = bit;                  // no second half
+                    }
+                } else {
+                    u32 s = s0idx, segEnd = 0, pieceStart = 0;
+                    SegmentDev sg{};
+#pragma unroll
+                    for (u32 j = 0; j < K; ++j) {
+                        if (j < nMine) {
+                            const u32 p = p0 + j;
+                            if (p >= segEnd) {
+                                if (segEnd) ++s;
+                                while (p >= segPieceStart[s + 1]) ++s;
+                                sg = seg[s]; pieceStart = segPieceStart[s]; segEnd = segPieceStart[s + 1];
+                            }
+                            const u32 bits = piece_bits(pk[j]);
+                            if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(cb[j]) << 32) | make_block_header(bit, piece_bpw(pk[j]), piece_dst(pk[j]));
+                            u32 half = 0;
+                            if (!sg.fill) {
+                                const u32 b = sg.block0 + (p - pieceStart);
+                                half = b > sg.last0 ? 1u : 0u;
+                                if (b == sg.last0 + 1) segMid[s] = bit;
+                                if (bits) {      // where the old stream continues for this half: the same from every piece of it
+                                    const u64 blk = __ldg(oldLeaf.blocks + b);
+                                    const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
+                                    u64 srcAt;
+                                    copy_piece(sg, b, blk, nextLocal, srcAt);
+                                    segDelta[half][s] = srcAt - bit;
+                                }
+                            }
+                            if (p == pieceStart) segBit0[s] = bit;
+                            bit += bits;
+                            if (p + 1 == segEnd) {
+                                segBit1[s] = bit;
+                                if (!half) segMid[s] = bit;                           // no second half
+                            }
                         }
                     }
                 }
@@ -406,7 +463,24 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
             const u32 q0 = skew + chunkBit0, q1 = skew + carryBits;
             const u32 w0 = q0 >> 5, w1 = (q1 - 1) >> 5;
             u32* out = weights + (tile.y >> 5);
+            // one COPY segment, everything about it in registers: a whole word that comes from one old macro block is two
+            // loads and a funnel shift; the others (first, last, across the old macro boundary) go the general way
+            const u32 mid0 = oneCopy ? segMid[0] : 0;
+            const u64 delta0 = oneCopy ? segDelta[0][0] : 0, delta1 = oneCopy ? segDelta[1][0] : 0;
             for (u32 w = w0 + t; w <= w1; w += T) {
+                if (oneCopy && (w << 5) >= q0 && ((w + 1) << 5) <= q1) {
+                    const u32 a = (w << 5) - skew;
+                    if (a + 32 <= mid0 || a >= mid0) {
+                        const u64 p = (a >= mid0 ? delta1 : delta0) + a;
+                        if ((p >> 5) + 1 < oldLeaf.nWeights) {
+                            const u32 shift = u32(p) & 31;
+                            const u32* src = oldLeaf.weights + (p >> 5);
+                            const u32 hi = __byte_perm(__ldg(src), 0, 0x0123), lo = shift ? __byte_perm(__ldg(src + 1), 0, 0x0123) : 0u;
+                            out[w] = __byte_perm(__funnelshift_l(lo, hi, shift), 0, 0x0123);
+                            continue;
+                        }
+                    }
+                }
                 const u32 a0 = max(q0, w << 5) - skew, b0 = min(q1, (w + 1) << 5) - skew;     // bits of the macro block in this word
                 u32 sgi = 0;                                 // first segment whose bits end after a0
                 if (nChunk > 1) {
@@ -417,18 +491,6 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
                     }
                 }
                 u32 v = 0;
-                if (b0 - a0 == 32 && !seg[sgi].fill) {       // the usual case: a whole word from one old macro block of one COPY segment
-                    const u32 mid = segMid[sgi];
-                    const bool in0 = a0 >= segBit0[sgi] && b0 <= mid, in1 = a0 >= mid && b0 <= segBit1[sgi];
-                    const u64 p = segDelta[in1 ? 1 : 0][sgi] + a0;
-                    if ((in0 || in1) && (p >> 5) + 1 < oldLeaf.nWeights) {
-                        const u32 sh = u32(p) & 31;
-                        const u32* src = oldLeaf.weights + (p >> 5);
-                        const u32 hi = __byte_perm(__ldg(src), 0, 0x0123), lo = sh ? __byte_perm(__ldg(src + 1), 0, 0x0123) : 0u;
-                        out[w] = __byte_perm(__funnelshift_l(lo, hi, sh), 0, 0x0123);
-                        continue;
-                    }
-                }
                 for (; sgi < nChunk && segBit0[sgi] < b0; ++sgi) {
                     if (max(a0, segBit0[sgi]) >= min(b0, segBit1[sgi])) continue;
                     const u32 fill = seg[sgi].fill;
@@ -453,7 +515,10 @@ __global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const Segme
         }
         __syncthreads();                                    // the segment arrays are rewritten by the next chunk
     }
-    if (!EMIT && t == 0) tiles[blockIdx.x] = TilePair{ carryBlocks, carryBits };
+    if (!EMIT && t == 0) {
+        tiles[blockIdx.x] = TilePair{ carryBlocks, carryBits };
+        atomicAdd(reinterpret_cast<unsigned long long*>(groupSums + blockIdx.x / kTileGroup), (u64(carryBlocks) << 32) | carryBits);
+    }
 }
 
 }  // namespace hdt

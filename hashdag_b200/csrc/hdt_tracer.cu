@@ -1628,8 +1628,8 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     // scratch: [ops][tile pairs][tile offsets][totals][segments][segments of each tile]
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
     const size_t offOps = 0, offTiles = align(dev.size() * sizeof(ColorOpDev));
-    const size_t offOffsets = offTiles + align(size_t(nTiles) * sizeof(TilePair)), offTotals = offOffsets + align(size_t(nTiles) * sizeof(ulonglong2));
-    const size_t offSegs = offTotals + 256, offTileSegs = offSegs + align((dev.size() + nTiles) * sizeof(SegmentDev));
+    const size_t offOffsets = offTiles + align(size_t(nTiles) * sizeof(TilePair)), offTotals = offOffsets + align((size_t(nTiles) + 1) * sizeof(ulonglong2));
+    const size_t offGroups = offTotals + 256, offSegs = offGroups + 256 * sizeof(u64), offTileSegs = offSegs + align((dev.size() + nTiles) * sizeof(SegmentDev));
     const size_t need = offTileSegs + align(size_t(nTiles) * sizeof(TileSegments));
     if (need > c->rebuildScratchBytes) {
         HDT_CUDA(cudaStreamSynchronize(c->stream));
@@ -1642,13 +1642,15 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     TilePair* dTiles = reinterpret_cast<TilePair*>(base + offTiles);
     ulonglong2* dOffsets = reinterpret_cast<ulonglong2*>(base + offOffsets);
     u64* dTotals = reinterpret_cast<u64*>(base + offTotals);
+    u64* dGroups = reinterpret_cast<u64*>(base + offGroups);     // sums of {blocks, bits} over groups of 256 macro blocks
     SegmentDev* dSegs = reinterpret_cast<SegmentDev*>(base + offSegs);
     TileSegments* dTileSegs = reinterpret_cast<TileSegments*>(base + offTileSegs);
     HDT_CUDA(cudaMemcpyAsync(dOps, dev.data(), dev.size() * sizeof(ColorOpDev), cudaMemcpyHostToDevice, c->stream));
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
     color_segments_kernel<<<(nTiles + 7) / 8, 256, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, nTiles, dSegs, dTileSegs);
-    color_pieces_kernel<false><<<nTiles, kPieceThreads, 0, c->stream>>>(dSegs, dTileSegs, leaf, dTiles, nullptr, nullptr, nullptr, nullptr);
-    scan_color_tiles_kernel<<<1, 1024, 0, c->stream>>>(dTiles, nTiles, dOffsets, dTotals);
+    HDT_CUDA(cudaMemsetAsync(dGroups, 0, 256 * sizeof(u64), c->stream));
+    color_pieces_kernel<false><<<nTiles, kPieceThreads, 0, c->stream>>>(dSegs, dTileSegs, leaf, dTiles, dGroups, nullptr, nullptr, nullptr, nullptr);
+    scan_color_tiles_kernel<<<(nTiles + kTileGroup - 1) / kTileGroup, kTileGroup, 0, c->stream>>>(dTiles, nTiles, dGroups, dOffsets, dTotals, weights_out, weights_out ? weights_capacity : 0);
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->launches += 3;
     u64 totals[2] = { 0, 0 };
@@ -1661,8 +1663,7 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
         return fail(HDT_ERR_CAPACITY, "hdt_rebuild_color_leaf: an output buffer is too small (see counts_out)");
     if ((counts_out[1] && !weights_out) || !blocks_out || !macro_blocks_out) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: null output buffer");
     HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    if (counts_out[1]) HDT_CUDA(cudaMemsetAsync(weights_out, 0, counts_out[1] * sizeof(u32), c->stream));
-    color_pieces_kernel<true><<<nTiles, kPieceThreads, 0, c->stream>>>(dSegs, dTileSegs, leaf, nullptr, dOffsets, weights_out, blocks_out, macro_blocks_out);
+    color_pieces_kernel<true><<<nTiles, kPieceThreads, 0, c->stream>>>(dSegs, dTileSegs, leaf, nullptr, nullptr, dOffsets, weights_out, blocks_out, macro_blocks_out);
     HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));

@@ -270,8 +270,11 @@ class HashDagReplica:
     """One GPU's copy of a HashDAG (+ colours) that follows edits through deltas.  Needs CUDA."""
 
     def __init__(self, tracer_obj, pool, page_table, pool_top, first_node_index, levels, pool_capacity_pages,
-                 color_nodes=None, color_offsets=None, main_leaf=None, color_node_capacity=0, device="cuda:0", resolved=True, replicate_from=None):
-        """replicate_from = r (tracer with a communicator): rank r's arrays are the truth -- the other ranks pass arrays of
+                 color_nodes=None, color_offsets=None, main_leaf=None, color_node_capacity=0, device="cuda:0", resolved=True, replicate_from=None,
+                 color_leaves=None):
+        """color_leaves: the unique colour leaves the colour tree already references (HashDAGColors::leaves, hash_dag_colors.h:65-73),
+        a sequence of tracer.CompressedColorLeaf (or None for unused slots) on `device`; later deltas replace entries.
+        replicate_from = r (tracer with a communicator): rank r's arrays are the truth -- the other ranks pass arrays of
         the same SIZES (contents ignored) and receive rank r's over hdt_replicate (initial replication)."""
         import torch
         from . import tracer as T
@@ -312,6 +315,13 @@ class HashDagReplica:
             self.leaves = {}                            # index -> tracer.CompressedColorLeaf (keeps the tensors alive)
             self.leaf_pods = None                       # int64 tensor, 13 words per leaf (CompressedColorLeaf, 104 B)
             self._pods_host = None                      # the same on the host, updated row by row
+            if color_leaves:
+                self._pods_host = np.zeros((len(color_leaves), 13), dtype=np.uint64)
+                for i, leaf in enumerate(color_leaves):
+                    if leaf is not None:
+                        self.leaves[i] = leaf
+                        self._pods_host[i] = np.frombuffer(leaf.pod(), dtype=np.uint64)
+                self.leaf_pods = T._to_device(self._pods_host.reshape(-1), device)
 
     def _replica_pod(self):
         T = self._T
