@@ -31,8 +31,17 @@
 
 namespace hdt {
 
-constexpr u32 kPieceThreads = 256;
-constexpr u32 kPiecesPerThread = 6;
+#ifndef HDT_PIECE_THREADS
+#define HDT_PIECE_THREADS 128
+#endif
+#ifndef HDT_PIECES_PER_THREAD
+#define HDT_PIECES_PER_THREAD 6
+#endif
+#ifndef HDT_PIECE_MIN_BLOCKS
+#define HDT_PIECE_MIN_BLOCKS 12     // <= 42 registers: the pass is latency bound, residency pays (profiles/r2_ab_color_leaf*.jsonl)
+#endif
+constexpr u32 kPieceThreads = HDT_PIECE_THREADS;
+constexpr u32 kPiecesPerThread = HDT_PIECES_PER_THREAD;
 
 // hdt_color_op with the exclusive prefix of the counts (where the op's first colour lands in the new leaf).
 struct ColorOpDev { u64 dstStart; u64 srcStart; u32 kind; u32 bitsPerWeight; u32 colorBits; u32 weight; };
@@ -252,7 +261,7 @@ __device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, 
 // rounds of a chunk every destination word of the chunk's bit range is put together by one thread from the segments that
 // overlap it (funnel shifts) and stored once.
 template<bool EMIT>
-__global__ void __launch_bounds__(kPieceThreads) color_pieces_kernel(const SegmentDev* __restrict__ segs, const TileSegments* __restrict__ tileSegs, const ColorLeafDev oldLeaf,
+__global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pieces_kernel(const SegmentDev* __restrict__ segs, const TileSegments* __restrict__ tileSegs, const ColorLeafDev oldLeaf,
                                                                       TilePair* __restrict__ tiles, u64* __restrict__ groupSums, const ulonglong2* __restrict__ offsets,
                                                                       u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
 {
