@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
         }
     }
     u32 carryBlocks = 0, carryBits = 0;          // blocks started / weight bits of this macro block so far (CTA-uniform)
-    u64 carryKey = 0;                            // key of the last piece so far
+    u64 carryKey = ~u64(0);                      // key of the last piece so far; no piece has this one: the first piece starts a block
     if (EMIT && nSeg > T) {
         // several chunks: the words two chunks share are put together with atomicOr as well.  Zero the macro block's words,
         // except the first and the last (shared with the neighbours, zeroed by the scan)
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
 #pragma unroll
             for (u32 j = 0; j < K; ++j) {
                 const u32 bpw = piece_bpw(pk[j]);
-                if (j < nMine && (piece_dst(pk[j]) == 0 || cb[j] != prevCb || bpw != prevBpw)) startsMask |= 1u << j;   // ColorLeafBuilder::add, vwsc.h:606
+                if (j < nMine && (cb[j] != prevCb || bpw != prevBpw)) startsMask |= 1u << j;   // ColorLeafBuilder::add, vwsc.h:606 (a macro block's first piece: carryKey)
                 prevCb = cb[j]; prevBpw = bpw;
             }
             // {blocks started, weight bits} in one word: a macro block has at most 65536 bits, a round at most T * K pieces
