@@ -8,6 +8,7 @@
 #   ncu                       ncu --set full of the three per-pixel kernels of a short bench run
 #   smoke                     __graft_entry__.smoke()
 #   colorleaf                 colour-leaf rebuild: its tests, scripts/bench_color_leaf.py, ncu --set full of its kernels
+#   sanitize <tool> <pytest args>   compute-sanitizer --tool memcheck|racecheck over a pytest selection
 #   golden <generator.py>     a tests/golden/make_*.py fixture generator (reference harness) -> gpurun_out/golden/
 set -x
 cd "$(dirname "$0")/.."
@@ -36,6 +37,9 @@ colorleaf)
     tail -c 1500 gpurun_out/${TAG}_color_leaf_bench.json
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:color_ -c 4 -f -o gpurun_out/${TAG}_cl_prof python scripts/bench_color_leaf.py --reps 1 > gpurun_out/${TAG}_cl_ncu.log 2>&1
     ncu -i gpurun_out/${TAG}_cl_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_cl_prof_raw.csv 2>/dev/null ;;
+sanitize)
+    tool=$1; shift
+    timeout 1500 compute-sanitizer --tool $tool --error-exitcode 7 --print-limit 20 python -m pytest "$@" -x -q 2>&1 | tail -40 | tee gpurun_out/${TAG}_sanitizer_${tool}.log ;;
 golden)
     timeout 900 python "$1" gpurun_out/golden 2>&1 | tail -20 | tee gpurun_out/${TAG}_golden.log ;;
 *)
