@@ -49,33 +49,31 @@ static_assert(sizeof(ColorOpDev) == 32, "uploaded as is");
 
 struct TilePair { u32 blocks; u32 bits; };   // per macro block: blocks started, weight bits appended
 
+// CTA-wide exclusive scan with ONE barrier: every warp leaves its sum in shared memory, every thread adds up the (few) warps in
+// front of it.  Two buffers, used alternately (`phase`, a per-thread counter all threads advance together): a warp can only
+// come back to a buffer after the barrier of the call in between, which every warp reaches after it has read this one.
 template<typename V>
-__device__ __forceinline__ V cta_exclusive_scan(V v, V& total)
+__device__ __forceinline__ V cta_exclusive_scan(V v, V& total, u32& phase)
 {
-    __shared__ V warpSums[32];
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ V warpSums[2][32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
     V inc = v;
 #pragma unroll
     for (u32 d = 1; d < 32; d <<= 1) {
         const V o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
         if (lane >= d) inc += o;
     }
-    if (lane == 31) warpSums[warp] = inc;
+    V* sums = warpSums[phase & 1];
+    ++phase;
+    if (lane == 31) sums[warp] = inc;
     __syncthreads();
-    if (warp == 0) {
-        const u32 nWarps = blockDim.x >> 5;
-        V w = lane < nWarps ? warpSums[lane] : V(0);
-#pragma unroll
-        for (u32 d = 1; d < 32; d <<= 1) {
-            const V o = __shfl_up_sync(0xFFFFFFFFu, w, d);
-            if (lane >= d) w += o;
-        }
-        warpSums[lane] = w;   // inclusive over warps
+    V base = V(0), all = V(0);
+    for (u32 w = 0; w < nWarps; ++w) {
+        const V x = sums[w];
+        if (w < warp) base += x;
+        all += x;
     }
-    __syncthreads();
-    const V base = warp ? warpSums[warp - 1] : V(0);
-    total = warpSums[(blockDim.x >> 5) - 1];
-    __syncthreads();          // warpSums may be reused by the caller's next scan
+    total = all;
     return base + inc - v;
 }
 
@@ -92,9 +90,10 @@ __global__ void __launch_bounds__(kTileGroup) scan_color_tiles_kernel(const Tile
     const TilePair mine = m < nTiles ? tiles[m] : TilePair{ 0, 0 };
     u64 front = t < g ? groupSums[t] : 0;            // at most 65536 / 256 = 256 groups
     u64 base;
-    cta_exclusive_scan(front, base);                 // (only the total is used)
+    u32 phase = 0;
+    cta_exclusive_scan(front, base, phase);          // (only the total is used)
     u64 total;
-    const u64 at = base + cta_exclusive_scan((u64(mine.blocks) << 32) | mine.bits, total);
+    const u64 at = base + cta_exclusive_scan((u64(mine.blocks) << 32) | mine.bits, total, phase);
     if (m < nTiles) {
         offsets[m] = make_ulonglong2(at >> 32, at & 0xFFFFFFFFull);
         const u64 word = (at & 0xFFFFFFFFull) >> 5;
@@ -123,6 +122,8 @@ __device__ __forceinline__ u32 find_block(const ColorLeafDev& l, u32 macro, u32 
     u32 lo = u32(__ldg(l.macroBlocks + 2 * u64(macro)));
     lastBlock = (2 * (u64(macro) + 1) < l.nMacroWords) ? u32(__ldg(l.macroBlocks + 2 * (u64(macro) + 1)) - 1) : u32(l.nBlocks - 1);
     u32 hi = lastBlock;
+    if (local == 0) return lo;                                   // a macro block's first colour is in its first block,
+    if (local == kColorsPerMacroBlock - 1) return hi;            // its last colour in its last (copies of whole macro blocks search nothing)
     while (lo < hi) {
         const u32 mid = (lo + hi + 1) >> 1;
         if ((u32(__ldg(l.blocks + mid)) & 0x3FFF) <= local) lo = mid; else hi = mid - 1;
@@ -137,6 +138,8 @@ __device__ __forceinline__ u32 find_block_warp(const ColorLeafDev& l, u32 macro,
     u32 lo = u32(__ldg(l.macroBlocks + 2 * u64(macro)));
     lastBlock = (2 * (u64(macro) + 1) < l.nMacroWords) ? u32(__ldg(l.macroBlocks + 2 * (u64(macro) + 1)) - 1) : u32(l.nBlocks - 1);
     u32 hi = lastBlock;                         // blocks[lo] starts at colour 0 <= local: the answer is in [lo, hi]
+    if (local == 0) return lo;
+    if (local == kColorsPerMacroBlock - 1) return hi;
     while (hi - lo >= 32) {
         const u32 step = (hi - lo) / 32;        // probes lo + step, lo + 2 step, ... lo + 32 step (<= hi)
         const u32 probe = lo + (lane + 1) * step;
@@ -238,6 +241,7 @@ __device__ __forceinline__ u64 piece_key(u32 colorBits, u32 pk) { return u64(col
 // macro block).  Colour indices are relative to the old macro block of the segment's first colour: the segment is
 // [src0, src0 + len) there, at most 16384 long, so it ends before 2 * 16384.  -> packed piece; srcAt = where its first weight
 // bit sits in the old stream.
+template<bool EMIT>
 __device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, u32 nextLocal, u64& srcAt)
 {
     const u32 second = b > sg.last0 ? 1u : 0u;
@@ -247,6 +251,7 @@ __device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, 
     const u32 blockStart = base + startLocal, blockEnd = base + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
     const u32 ps = max(blockStart, sg.src0), pe = min(blockEnd, sg.src0 + sg.len);
     const u32 bpw = block_bits_per_weight(hdr);
+    if (!EMIT) return pack_piece(0, bpw, pe - ps);               // the count pass needs neither position
     srcAt = (second ? sg.weightBase[1] : sg.weightBase[0]) + (hdr >> 16) + (ps - blockStart) * bpw;
     return pack_piece(sg.dstLocal + (ps - sg.src0), bpw, pe - ps);
 }
@@ -287,6 +292,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
         }
     }
     u32 carryBlocks = 0, carryBits = 0;          // blocks started / weight bits of this macro block so far (CTA-uniform)
+    u32 scanPhase = 0;
     u64 carryKey = ~u64(0);                      // key of the last piece so far; no piece has this one: the first piece starts a block
     if (EMIT && nSeg > T) {
         // several chunks: the words two chunks share are put together with atomicOr as well.  Zero the macro block's words,
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
             myPieces = sg.nPieces;
         }
         u32 totalPieces;
-        const u32 myStart = cta_exclusive_scan(myPieces, totalPieces);
+        const u32 myStart = cta_exclusive_scan(myPieces, totalPieces, scanPhase);
         if (t < nChunk) segPieceStart[t] = myStart;
         if (t == 0) segPieceStart[nChunk] = totalPieces;
         __syncthreads();
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                 for (u32 j = 0; j < K; ++j) {
                     if (j < nMine) {
                         u64 srcAt;
-                        pk[j] = copy_piece(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, srcAt);
+                        pk[j] = copy_piece<EMIT>(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, srcAt);
                         cb[j] = u32(blk[j] >> 32);
                         const u32 bits = piece_bits(pk[j]), half = b + j > sg.last0 ? 1u : 0u;
                         if (EMIT && bits && !(haveAt & (1u << half))) {
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                             const u64 blk = __ldg(oldLeaf.blocks + b);
                             const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
                             u64 srcAt;
-                            pk[j] = copy_piece(sg, b, blk, nextLocal, srcAt);
+                            pk[j] = copy_piece<EMIT>(sg, b, blk, nextLocal, srcAt);
                             cb[j] = u32(blk >> 32);
                         } else {
                             pk[j] = pack_piece(sg.dstLocal, (sg.fill >> 8) & 0xFF, sg.len);
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
             // {blocks started, weight bits} in one word: a macro block has at most 65536 bits, a round at most T * K pieces
             static_assert(T * K < 4096, "12 bits for the blocks a round starts");
             u32 total;
-            const u32 excl = cta_exclusive_scan((u32(__popc(startsMask)) << 20) | myBits, total);
+            const u32 excl = cta_exclusive_scan((u32(__popc(startsMask)) << 20) | myBits, total, scanPhase);
             const u32 nInRound = min(T * K, totalPieces - pBase);
             const u64 roundLastKey = lastKeyOf[(nInRound - 1) / K];
             if (EMIT && nMine) {
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                                     const u64 blk = __ldg(oldLeaf.blocks + b);
                                     const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
                                     u64 srcAt;
-                                    copy_piece(sg, b, blk, nextLocal, srcAt);
+                                    copy_piece<true>(sg, b, blk, nextLocal, srcAt);
                                     segDelta[half][s] = srcAt - bit;
                                 }
                             }

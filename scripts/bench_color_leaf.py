@@ -62,6 +62,13 @@ def main():
     out["whole"] = {"colours": n, "kernel_ms": med, "kernel_ms_best": best, "call_wall_ms": wall, "mcolours_s": n / med / 1e3,
                     "algorithmic_bytes": in_bytes + out_bytes, "achieved_GBps": (in_bytes + out_bytes) / med / 1e6, "peak_GBps": peak,
                     "frac": (in_bytes + out_bytes) / med / 1e6 / peak, "blocks": int(leaf.blocks.numel()), "weight_words": int(nw)}
+    # the same leaf from colour 5000 on: no macro block of the new leaf lines up with one of the old leaf (every segment is searched for,
+    # spans two old macro blocks, and its weights move by a bit offset)
+    u = host.ColorLeafBuilder()
+    u.copy_colors(5000, n - 5000)
+    _, umed, ubest = run(u, a.reps)
+    out["whole_unaligned"] = {"colours": n - 5000, "kernel_ms": umed, "kernel_ms_best": ubest, "mcolours_s": (n - 5000) / umed / 1e3,
+                              "frac": (in_bytes + out_bytes) / umed / 1e6 / peak}
     # parity on the sample the CPU baseline encodes
     ns = min(a.cpu_sample, n)
     c0 = time.perf_counter()
