@@ -249,9 +249,16 @@ __device__ __forceinline__ void shadow_ray(const CameraParams& cam, const Shadow
     double rm[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double t0 = __ddiv_rn(__dsub_rn(bo[k], cam.cam[k]), dv[k]);
-        const double t1 = __ddiv_rn(__dsub_rn(__dadd_rn(bo[k], 1.0), cam.cam[k]), dv[k]);
-        rm[k] = (t0 < t1) ? t0 : t1;
+        // tracer.cu:578-581 takes the smaller of t0 = (lo - cam) / d and t1 = (lo + 1 - cam) / d.  Correctly rounded subtraction and
+        // division are monotone, and the numerators differ by one while |d| <= 1, so t0 < t1 exactly when d > 0 and t1 < t0 when
+        // d < 0: one division gives the minimum.  (d = 0 or NaN: both, as written there.)
+        const double n0 = __dsub_rn(bo[k], cam.cam[k]), n1 = __dsub_rn(__dadd_rn(bo[k], 1.0), cam.cam[k]);
+        if (dv[k] > 0.0) rm[k] = __ddiv_rn(n0, dv[k]);
+        else if (dv[k] < 0.0) rm[k] = __ddiv_rn(n1, dv[k]);
+        else {
+            const double t0 = __ddiv_rn(n0, dv[k]), t1 = __ddiv_rn(n1, dv[k]);
+            rm[k] = (t0 < t1) ? t0 : t1;
+        }
     }
     const double maxmin = fmax(fmax(rm[0], rm[1]), rm[2]);
     ray.ox = __fmaf_rn(sp.shadowBias, sp.sunX, __double2float_rn(__fma_rn(dv[0], maxmin, cam.cam[0])));
