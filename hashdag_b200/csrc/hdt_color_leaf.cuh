@@ -47,7 +47,7 @@ constexpr u32 kPiecesPerThread = HDT_PIECES_PER_THREAD;
 struct ColorOpDev { u64 dstStart; u64 srcStart; u32 kind; u32 bitsPerWeight; u32 colorBits; u32 weight; };
 static_assert(sizeof(ColorOpDev) == 32, "uploaded as is");
 
-struct TilePair { u32 blocks; u32 bits; };   // per macro block: blocks started, weight bits appended
+struct TilePieces { u32 stageBase, blocks, bits, pad; };   // per macro block: where its finished block entries are staged, how many, weight bits
 
 // CTA-wide exclusive scan with ONE barrier: every warp leaves its sum in shared memory, every thread adds up the (few) warps in
 // front of it.  Two buffers, used alternately (`phase`, a per-thread counter all threads advance together): a warp can only
@@ -83,11 +83,11 @@ __device__ __forceinline__ V cta_exclusive_scan(V v, V& total, u32& phase)
 // The weight words two macro blocks share (the word a macro block's first bit falls into) are put together with atomicOr by
 // the emit pass: they are zeroed here, if the caller's buffer reaches that far.
 constexpr u32 kTileGroup = 256;
-__global__ void __launch_bounds__(kTileGroup) scan_color_tiles_kernel(const TilePair* __restrict__ tiles, const u32 nTiles, const u64* __restrict__ groupSums,
+__global__ void __launch_bounds__(kTileGroup) scan_color_tiles_kernel(const TilePieces* __restrict__ tiles, const u32 nTiles, const u64* __restrict__ groupSums,
                                                                        ulonglong2* __restrict__ offsets, u64* __restrict__ totals, u32* __restrict__ weights, const u64 weightsCapacity)
 {
     const u32 t = threadIdx.x, g = blockIdx.x, m = g * kTileGroup + t;
-    const TilePair mine = m < nTiles ? tiles[m] : TilePair{ 0, 0 };
+    const TilePieces mine = m < nTiles ? tiles[m] : TilePieces{ 0, 0, 0, 0 };
     u64 front = t < g ? groupSums[t] : 0;            // at most 65536 / 256 = 256 groups
     u64 base;
     u32 phase = 0;
@@ -241,7 +241,6 @@ __device__ __forceinline__ u64 piece_key(u32 colorBits, u32 pk) { return u64(col
 // macro block).  Colour indices are relative to the old macro block of the segment's first colour: the segment is
 // [src0, src0 + len) there, at most 16384 long, so it ends before 2 * 16384.  -> packed piece; srcAt = where its first weight
 // bit sits in the old stream.
-template<bool EMIT>
 __device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, u32 nextLocal, u64& srcAt)
 {
     const u32 second = b > sg.last0 ? 1u : 0u;
@@ -251,60 +250,54 @@ __device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, 
     const u32 blockStart = base + startLocal, blockEnd = base + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
     const u32 ps = max(blockStart, sg.src0), pe = min(blockEnd, sg.src0 + sg.len);
     const u32 bpw = block_bits_per_weight(hdr);
-    if (!EMIT) return pack_piece(0, bpw, pe - ps);               // the count pass needs neither position
     srcAt = (second ? sg.weightBase[1] : sg.weightBase[0]) + (hdr >> 16) + (ps - blockStart) * bpw;
     return pack_piece(sg.dstLocal + (ps - sg.src0), bpw, pe - ps);
 }
 
-// One CTA per macro block of the new leaf.  EMIT = false: tiles[blockIdx] = {blocks started, weight bits}.  EMIT = true: the
-// macro block is written (offsets[blockIdx] = its first block index and weight bit offset; `weights` zeroed beforehand).
+// Where a segment's weight bits go and come from, relative to the new macro block: bits [bit0, mid) are the old stream's
+// bits from (bit + delta[0]) on, bits [mid, bit1) from (bit + delta[1]) on -- a segment touches at most two macro blocks of the
+// old leaf, and the old stream need not be contiguous across them (the format lets a builder pad there).  FILL: `fill` as in
+// SegmentDev, a periodic pattern.  Written by the pieces pass, read by the emit pass.
+struct SegmentWeights { u32 bit0, mid, bit1, fill; u64 delta[2]; };
+static_assert(sizeof(SegmentWeights) == 32, "two 16-byte loads");
+
+// Pass 1, one CTA per macro block of the new leaf: everything that is per piece, once.  The block entries of a macro block do not
+// depend on where the macro block ends up (weight offset and colour index are relative to it), so they are finished here and
+// staged (`stage`, space taken from `stageTop`); so are its segments' weight ranges.  What is still unknown -- the macro block's
+// first block index and weight bit offset -- comes from the scan of the {blocks, bits} pairs this pass leaves in `tiles`.
 //
 // The segments of the macro block are taken T at a time (a "chunk", one per thread), the pieces of a chunk T*K at a time (a
-// "round": K consecutive pieces per thread, one CTA-wide scan of {blocks started, weight bits}).  The weights are not moved piece
-// by piece: the pieces of a COPY segment are consecutive blocks of the old leaf, so the segment's weights are one contiguous bit
-// range of the old stream per old macro block it touches (at most two), and a FILL segment is a periodic pattern.  After the
-// rounds of a chunk every destination word of the chunk's bit range is put together by one thread from the segments that
-// overlap it (funnel shifts) and stored once.
-template<bool EMIT>
+// "round": K consecutive pieces per thread, one CTA-wide scan of {blocks started, weight bits}).
 __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pieces_kernel(const SegmentDev* __restrict__ segs, const TileSegments* __restrict__ tileSegs, const ColorLeafDev oldLeaf,
-                                                                      TilePair* __restrict__ tiles, u64* __restrict__ groupSums, const ulonglong2* __restrict__ offsets,
-                                                                      u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
+                                                                      TilePieces* __restrict__ tiles, u64* __restrict__ groupSums, u64* __restrict__ stage, u32* __restrict__ stageTop,
+                                                                      SegmentWeights* __restrict__ segWeights)
 {
     constexpr u32 T = kPieceThreads, K = kPiecesPerThread;
     __shared__ SegmentDev seg[T];
     __shared__ u32 segPieceStart[T + 1];    // exclusive prefix of the pieces per segment
     __shared__ u64 lastKeyOf[T];            // key of each thread's last piece of the round
-    // weight bits of the segments, relative to the macro block: bits [segBit0, segMid) come from the old stream at (bit + segDelta[0]),
-    // bits [segMid, segBit1) from (bit + segDelta[1]) -- the stream of the old leaf need not be contiguous across its macro blocks
-    // (the format lets a builder pad there)
-    __shared__ u32 segBit0[EMIT ? T : 1], segMid[EMIT ? T : 1], segBit1[EMIT ? T : 1];
-    __shared__ u64 segDelta[EMIT ? 2 : 1][EMIT ? T : 1];
+    __shared__ u32 segBit0[T], segMid[T], segBit1[T];
+    __shared__ u64 segDelta[2][T];
+    __shared__ u32 stageBaseShared;
 
     const u32 t = threadIdx.x;
     const TileSegments mine = tileSegs[blockIdx.x];
     const u32 nSeg = mine.count;
-    ulonglong2 tile = make_ulonglong2(0, 0);
-    if (EMIT) {
-        tile = offsets[blockIdx.x];
-        if (t == 0) {   // MacroBlockStruct, vwsc.h:595-599 / build() :677-681
-            macroBlocks[2 * u64(blockIdx.x)] = tile.x;
-            macroBlocks[2 * u64(blockIdx.x) + 1] = tile.y;
-        }
-    }
     u32 carryBlocks = 0, carryBits = 0;          // blocks started / weight bits of this macro block so far (CTA-uniform)
     u32 scanPhase = 0;
     u64 carryKey = ~u64(0);                      // key of the last piece so far; no piece has this one: the first piece starts a block
-    if (EMIT && nSeg > T) {
-        // several chunks: the words two chunks share are put together with atomicOr as well.  Zero the macro block's words,
-        // except the first and the last (shared with the neighbours, zeroed by the scan)
-        const u64 endBit = offsets[blockIdx.x + 1].y;
-        for (u64 w = (tile.y >> 5) + 1 + t; w + 1 <= (endBit >> 5); w += T) weights[w] = 0;
+    {   // room for the macro block's block entries: at most one per piece
+        u32 pieces = 0;
+        for (u32 k = t; k < nSeg; k += T) pieces += segs[mine.first + k].nPieces;
+        u32 total;
+        cta_exclusive_scan(pieces, total, scanPhase);
+        if (t == 0) stageBaseShared = atomicAdd(stageTop, total);
         __syncthreads();
     }
+    const u32 stageBase = stageBaseShared;
 
     for (u32 segBase = 0; segBase < nSeg; segBase += T) {
         const u32 nChunk = min(T, nSeg - segBase);
-        const u32 chunkBit0 = carryBits;
         // ---- segments of this chunk ----
         u32 myPieces = 0;
         if (t < nChunk) {
@@ -332,7 +325,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
             }
             u32 cb[K], pk[K];                    // the thread's pieces: colorBits, pack_piece()
             u32 myBits = 0;
-            // oneCopy, EMIT: where the old stream continues for the thread's first weighted piece of each half of the segment
+            // oneCopy: where the old stream continues for the thread's first weighted piece of each half of the segment
             // (position of that piece's first bit minus the thread's bits in front of it), and which halves it has
             u64 at0 = 0, at1 = 0;
             u32 haveAt = 0;
@@ -343,17 +336,17 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                 const SegmentDev sg = seg[0];
                 const u32 b = sg.block0 + p0;
                 u64 blk[K + 1];
-#pragma unroll
                 const u32 nLoad = u32(min(u64(nMine) + 1, oldLeaf.nBlocks - b));   // (b < nBlocks: the thread has pieces)
+#pragma unroll
                 for (u32 j = 0; j <= K; ++j) blk[j] = j < nLoad ? __ldg(oldLeaf.blocks + b + j) : 0;
 #pragma unroll
                 for (u32 j = 0; j < K; ++j) {
                     if (j < nMine) {
                         u64 srcAt;
-                        pk[j] = copy_piece<EMIT>(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, srcAt);
+                        pk[j] = copy_piece(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, srcAt);
                         cb[j] = u32(blk[j] >> 32);
                         const u32 bits = piece_bits(pk[j]), half = b + j > sg.last0 ? 1u : 0u;
-                        if (EMIT && bits && !(haveAt & (1u << half))) {
+                        if (bits && !(haveAt & (1u << half))) {
                             if (half) at1 = srcAt - myBits; else at0 = srcAt - myBits;
                             haveAt |= 1u << half;
                         }
@@ -378,7 +371,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                             const u64 blk = __ldg(oldLeaf.blocks + b);
                             const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
                             u64 srcAt;
-                            pk[j] = copy_piece<EMIT>(sg, b, blk, nextLocal, srcAt);
+                            pk[j] = copy_piece(sg, b, blk, nextLocal, srcAt);
                             cb[j] = u32(blk >> 32);
                         } else {
                             pk[j] = pack_piece(sg.dstLocal, (sg.fill >> 8) & 0xFF, sg.len);
@@ -410,8 +403,8 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
             const u32 excl = cta_exclusive_scan((u32(__popc(startsMask)) << 20) | myBits, total, scanPhase);
             const u32 nInRound = min(T * K, totalPieces - pBase);
             const u64 roundLastKey = lastKeyOf[(nInRound - 1) / K];
-            if (EMIT && nMine) {
-                u64 blockIndex = tile.x + carryBlocks + (excl >> 20);
+            if (nMine) {
+                u64* out = stage + stageBase + carryBlocks + (excl >> 20);
                 u32 bit = carryBits + (excl & 0xFFFFF);     // weight bit offset relative to the macro block
                 if (oneCopy) {
                     const u32 b = seg[0].block0 + p0, last0 = seg[0].last0;
@@ -421,7 +414,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
 #pragma unroll
                     for (u32 j = 0; j < K; ++j) {
                         if (j < nMine) {
-                            if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(cb[j]) << 32) | make_block_header(bit, piece_bpw(pk[j]), piece_dst(pk[j]));
+                            if (startsMask & (1u << j)) *out++ = (u64(cb[j]) << 32) | make_block_header(bit, piece_bpw(pk[j]), piece_dst(pk[j]));
                             if (b + j == last0 + 1) segMid[0] = bit;                  // the first piece from the second old macro block
                             bit += piece_bits(pk[j]);
                         }
@@ -443,7 +436,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                                 sg = seg[s]; pieceStart = segPieceStart[s]; segEnd = segPieceStart[s + 1];
                             }
                             const u32 bits = piece_bits(pk[j]);
-                            if (startsMask & (1u << j)) blocks[blockIndex++] = (u64(cb[j]) << 32) | make_block_header(bit, piece_bpw(pk[j]), piece_dst(pk[j]));
+                            if (startsMask & (1u << j)) *out++ = (u64(cb[j]) << 32) | make_block_header(bit, piece_bpw(pk[j]), piece_dst(pk[j]));
                             u32 half = 0;
                             if (!sg.fill) {
                                 const u32 b = sg.block0 + (p - pieceStart);
@@ -453,7 +446,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                                     const u64 blk = __ldg(oldLeaf.blocks + b);
                                     const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
                                     u64 srcAt;
-                                    copy_piece<true>(sg, b, blk, nextLocal, srcAt);
+                                    copy_piece(sg, b, blk, nextLocal, srcAt);
                                     segDelta[half][s] = srcAt - bit;
                                 }
                             }
@@ -470,18 +463,75 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
             carryBlocks += total >> 20;
             carryBits += total & 0xFFFFF;
             carryKey = roundLastKey;
-            __syncthreads();                                // lastKeyOf is rewritten by the next round
+            __syncthreads();                                // lastKeyOf is rewritten by the next round; the chunk's weight ranges are complete
         }
-        // ---- weights of this chunk: destination words [w0, w1] of the macro block's bit range [chunkBit0, carryBits) ----
-        if (EMIT && carryBits > chunkBit0) {
-            const u32 skew = u32(tile.y & 31);              // the macro block's first bit within its first word
-            const u32 q0 = skew + chunkBit0, q1 = skew + carryBits;
+        if (t < nChunk) segWeights[mine.first + segBase + t] = SegmentWeights{ segBit0[t], segMid[t], segBit1[t], seg[t].fill, { segDelta[0][t], segDelta[1][t] } };
+        __syncthreads();                                    // the segment arrays are rewritten by the next chunk
+    }
+    if (t == 0) {
+        tiles[blockIdx.x] = TilePieces{ stageBase, carryBlocks, carryBits, 0 };
+        atomicAdd(reinterpret_cast<unsigned long long*>(groupSums + blockIdx.x / kTileGroup), (u64(carryBlocks) << 32) | carryBits);
+    }
+}
+
+// Pass 2, one CTA per macro block, nothing per piece: the staged block entries go to their place, the macro-block pair is written,
+// and the weights are moved: every destination word of the macro block is put together by one thread from the segments that
+// overlap it (a COPY segment's weights are a contiguous bit range of the old stream per old macro block: funnel shifts) and
+// stored once; the words shared with a neighbouring macro block or chunk go through atomicOr (zeroed by the scan / below).
+#ifndef HDT_EMIT_THREADS
+#define HDT_EMIT_THREADS 128
+#endif
+constexpr u32 kEmitThreads = HDT_EMIT_THREADS;
+__global__ void __launch_bounds__(kEmitThreads) color_emit_kernel(const SegmentWeights* __restrict__ segWeights, const TileSegments* __restrict__ tileSegs,
+                                                                   const TilePieces* __restrict__ tiles, const u64* __restrict__ stage, const ulonglong2* __restrict__ offsets,
+                                                                   const ColorLeafDev oldLeaf, u32* __restrict__ weights, u64* __restrict__ blocks, u64* __restrict__ macroBlocks)
+{
+    constexpr u32 T = kEmitThreads;
+    __shared__ SegmentWeights sw[T];
+    const u32 t = threadIdx.x;
+    const ulonglong2 tile = offsets[blockIdx.x];
+    const TilePieces mine = tiles[blockIdx.x];
+    const TileSegments segsOf = tileSegs[blockIdx.x];
+    if (t == 0) {   // MacroBlockStruct, vwsc.h:595-599 / build() :677-681
+        macroBlocks[2 * u64(blockIdx.x)] = tile.x;
+        macroBlocks[2 * u64(blockIdx.x) + 1] = tile.y;
+    }
+    const u32 nSeg = segsOf.count;
+    if (t < min(T, nSeg)) sw[t] = segWeights[segsOf.first + t];   // the first chunk's weight ranges, in flight beside the copy below
+    {   // four entries in flight per thread
+        const u64* from = stage + mine.stageBase;
+        u64* to = blocks + tile.x;
+        u32 k = t;
+        for (; k + 3 * T < mine.blocks; k += 4 * T) {
+            const u64 e0 = __ldg(from + k), e1 = __ldg(from + k + T), e2 = __ldg(from + k + 2 * T), e3 = __ldg(from + k + 3 * T);
+            to[k] = e0; to[k + T] = e1; to[k + 2 * T] = e2; to[k + 3 * T] = e3;
+        }
+        for (; k < mine.blocks; k += T) to[k] = __ldg(from + k);
+    }
+    if (mine.bits == 0) return;
+    const u32 skew = u32(tile.y & 31);                      // the macro block's first bit within its first word
+    u32* out = weights + (tile.y >> 5);
+    if (nSeg > T) {
+        // several chunks: the words two chunks share are put together with atomicOr as well.  Zero the macro block's words,
+        // except the first and the last (shared with the neighbours, zeroed by the scan)
+        const u64 endBit = offsets[blockIdx.x + 1].y;
+        for (u64 w = (tile.y >> 5) + 1 + t; w + 1 <= (endBit >> 5); w += T) weights[w] = 0;
+        __syncthreads();
+    }
+    for (u32 segBase = 0; segBase < nSeg; segBase += T) {
+        const u32 nChunk = min(T, nSeg - segBase);
+        if (segBase && t < nChunk) sw[t] = segWeights[segsOf.first + segBase + t];
+        __syncthreads();
+        const u32 chunkBit0 = sw[0].bit0, chunkBit1 = sw[nChunk - 1].bit1;
+        if (chunkBit1 > chunkBit0) {
+            const u32 q0 = skew + chunkBit0, q1 = skew + chunkBit1;
             const u32 w0 = q0 >> 5, w1 = (q1 - 1) >> 5;
-            u32* out = weights + (tile.y >> 5);
             // one COPY segment, everything about it in registers: a whole word that comes from one old macro block is two
             // loads and a funnel shift; the others (first, last, across the old macro boundary) go the general way
-            const u32 mid0 = oneCopy ? segMid[0] : 0;
-            const u64 delta0 = oneCopy ? segDelta[0][0] : 0, delta1 = oneCopy ? segDelta[1][0] : 0;
+            const bool oneCopy = nChunk == 1 && !sw[0].fill;
+            const u32 mid0 = sw[0].mid;
+            const u64 delta0 = sw[0].delta[0], delta1 = sw[0].delta[1];
+#pragma unroll 4
             for (u32 w = w0 + t; w <= w1; w += T) {
                 if (oneCopy && (w << 5) >= q0 && ((w + 1) << 5) <= q1) {
                     const u32 a = (w << 5) - skew;
@@ -502,25 +552,25 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                     u32 e = nChunk - 1;
                     while (sgi < e) {
                         const u32 mid = (sgi + e) >> 1;
-                        if (segBit1[mid] > a0) e = mid; else sgi = mid + 1;
+                        if (sw[mid].bit1 > a0) e = mid; else sgi = mid + 1;
                     }
                 }
                 u32 v = 0;
-                for (; sgi < nChunk && segBit0[sgi] < b0; ++sgi) {
-                    if (max(a0, segBit0[sgi]) >= min(b0, segBit1[sgi])) continue;
-                    const u32 fill = seg[sgi].fill;
-                    if (!fill) {
+                for (; sgi < nChunk && sw[sgi].bit0 < b0; ++sgi) {
+                    const SegmentWeights g = sw[sgi];
+                    if (max(a0, g.bit0) >= min(b0, g.bit1)) continue;
+                    if (!g.fill) {
 #pragma unroll
                         for (u32 half = 0; half < 2; ++half) {
-                            const u32 a = max(a0, half ? segMid[sgi] : segBit0[sgi]), b = min(b0, half ? segBit1[sgi] : segMid[sgi]);
-                            if (a < b) v |= read_stream_bits(oldLeaf, segDelta[half][sgi] + a, b - a) >> ((a + skew) & 31);
+                            const u32 a = max(a0, half ? g.mid : g.bit0), b = min(b0, half ? g.bit1 : g.mid);
+                            if (a < b) v |= read_stream_bits(oldLeaf, (half ? g.delta[1] : g.delta[0]) + a, b - a) >> ((a + skew) & 31);
                         }
                     } else {                                 // the stream of a repeated weight, from the phase this word starts in
-                        const u32 a = max(a0, segBit0[sgi]), b = min(b0, segBit1[sgi]);
-                        const u32 bpw = (fill >> 8) & 0xFF;
+                        const u32 a = max(a0, g.bit0), b = min(b0, g.bit1);
+                        const u32 bpw = (g.fill >> 8) & 0xFF;
                         u64 pat = 0;
-                        for (u32 k = 0; k < 64; k += bpw) pat |= (u64(fill >> 16) << (64 - bpw)) >> k;
-                        v |= (u32((pat << ((a - segBit0[sgi]) % bpw)) >> 32) & (0xFFFFFFFFu << (32 - (b - a)))) >> ((a + skew) & 31);
+                        for (u32 k = 0; k < 64; k += bpw) pat |= (u64(g.fill >> 16) << (64 - bpw)) >> k;
+                        v |= (u32((pat << ((a - g.bit0) % bpw)) >> 32) & (0xFFFFFFFFu << (32 - (b - a)))) >> ((a + skew) & 31);
                     }
                 }
                 v = __byte_perm(v, 0, 0x0123);               // ColorUtils::swap_byte_order, build() :671-674
@@ -528,11 +578,7 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                 else if (v) atomicOr(out + w, v);            // shared with the neighbouring chunk or macro block
             }
         }
-        __syncthreads();                                    // the segment arrays are rewritten by the next chunk
-    }
-    if (!EMIT && t == 0) {
-        tiles[blockIdx.x] = TilePair{ carryBlocks, carryBits };
-        atomicAdd(reinterpret_cast<unsigned long long*>(groupSums + blockIdx.x / kTileGroup), (u64(carryBlocks) << 32) | carryBits);
+        __syncthreads();                                    // `sw` is rewritten by the next chunk
     }
 }
 

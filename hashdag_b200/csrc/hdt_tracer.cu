@@ -1601,7 +1601,7 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     // op list -> device form: empty ops dropped, exclusive prefix of the counts, one sentinel
     std::vector<ColorOpDev> dev;
     dev.reserve(n_ops + 1);
-    u64 n = 0;
+    u64 n = 0, piecesBound = 0;       // pieces: runs of one old block / one FILL op (cut again at the new macro blocks: + one per segment)
     bool copies = false;
     for (u64 i = 0; i < n_ops; ++i) {
         const hdt_color_op& o = ops[i];
@@ -1617,6 +1617,7 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
                 return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: COPY op reaches beyond the old leaf's macro blocks");
         }
         copies |= o.kind == HDT_COLOR_OP_COPY;
+        piecesBound += o.kind == HDT_COLOR_OP_FILL ? 1 : std::min<u64>(o.count, old_leaf ? old_leaf->blocks_gpu.size : 0);
         dev.push_back(ColorOpDev{ n, o.src_start, o.kind, o.bits_per_weight, o.color_bits, o.weight });
         n += o.count;
     }
@@ -1632,31 +1633,38 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
     dev.push_back(ColorOpDev{ n, 0, HDT_COLOR_OP_FILL, 0, 0, 0 });
     const u32 nTiles = u32((n + kColorsPerMacroBlock - 1) / kColorsPerMacroBlock);
     HDT_CUDA(cudaSetDevice(c->device));
-    // scratch: [ops][tile pairs][tile offsets][totals][segments][segments of each tile]
+    // scratch: [ops][per macro block: pieces, offsets, segments][totals, group sums, stage top][segments, their weight ranges][staged block entries]
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t nSlots = dev.size() + nTiles;               // segment slots (color_segments_kernel)
+    const u64 stageEntries = piecesBound + nSlots;           // a macro block stages at most one block entry per piece
+    if (stageEntries >= (u64(1) << 32)) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: too many pieces");
     const size_t offOps = 0, offTiles = align(dev.size() * sizeof(ColorOpDev));
-    const size_t offOffsets = offTiles + align(size_t(nTiles) * sizeof(TilePair)), offTotals = offOffsets + align((size_t(nTiles) + 1) * sizeof(ulonglong2));
-    const size_t offGroups = offTotals + 256, offSegs = offGroups + 256 * sizeof(u64), offTileSegs = offSegs + align((dev.size() + nTiles) * sizeof(SegmentDev));
-    const size_t need = offTileSegs + align(size_t(nTiles) * sizeof(TileSegments));
+    const size_t offOffsets = offTiles + align(size_t(nTiles) * sizeof(TilePieces)), offTileSegs = offOffsets + align((size_t(nTiles) + 1) * sizeof(ulonglong2));
+    const size_t offTotals = offTileSegs + align(size_t(nTiles) * sizeof(TileSegments)), offGroups = offTotals + 256, offStageTop = offGroups + 256 * sizeof(u64);
+    const size_t offSegs = offStageTop + 256, offSegWeights = offSegs + align(nSlots * sizeof(SegmentDev)), offStage = offSegWeights + align(nSlots * sizeof(SegmentWeights));
+    const size_t need = offStage + align(stageEntries * sizeof(u64));
     if (need > c->rebuildScratchBytes) {
         HDT_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(c->rebuildScratch); c->rebuildScratch = nullptr; c->rebuildScratchBytes = 0;
-        HDT_CUDA(cudaMalloc(&c->rebuildScratch, need + need / 2));
-        c->rebuildScratchBytes = need + need / 2;
+        HDT_CUDA(cudaMalloc(&c->rebuildScratch, need + need / 8));
+        c->rebuildScratchBytes = need + need / 8;
     }
     char* base = static_cast<char*>(c->rebuildScratch);
     ColorOpDev* dOps = reinterpret_cast<ColorOpDev*>(base + offOps);
-    TilePair* dTiles = reinterpret_cast<TilePair*>(base + offTiles);
+    TilePieces* dTiles = reinterpret_cast<TilePieces*>(base + offTiles);
     ulonglong2* dOffsets = reinterpret_cast<ulonglong2*>(base + offOffsets);
+    TileSegments* dTileSegs = reinterpret_cast<TileSegments*>(base + offTileSegs);
     u64* dTotals = reinterpret_cast<u64*>(base + offTotals);
     u64* dGroups = reinterpret_cast<u64*>(base + offGroups);     // sums of {blocks, bits} over groups of 256 macro blocks
+    u32* dStageTop = reinterpret_cast<u32*>(base + offStageTop);
     SegmentDev* dSegs = reinterpret_cast<SegmentDev*>(base + offSegs);
-    TileSegments* dTileSegs = reinterpret_cast<TileSegments*>(base + offTileSegs);
+    SegmentWeights* dSegWeights = reinterpret_cast<SegmentWeights*>(base + offSegWeights);
+    u64* dStage = reinterpret_cast<u64*>(base + offStage);
     HDT_CUDA(cudaMemcpyAsync(dOps, dev.data(), dev.size() * sizeof(ColorOpDev), cudaMemcpyHostToDevice, c->stream));
     HDT_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    HDT_CUDA(cudaMemsetAsync(dGroups, 0, 256 * sizeof(u64) + 256, c->stream));   // group sums and the stage top
     color_segments_kernel<<<(nTiles + 7) / 8, 256, 0, c->stream>>>(dOps, u32(dev.size() - 1), leaf, n, nTiles, dSegs, dTileSegs);
-    HDT_CUDA(cudaMemsetAsync(dGroups, 0, 256 * sizeof(u64), c->stream));
-    color_pieces_kernel<false><<<nTiles, kPieceThreads, 0, c->stream>>>(dSegs, dTileSegs, leaf, dTiles, dGroups, nullptr, nullptr, nullptr, nullptr);
+    color_pieces_kernel<<<nTiles, kPieceThreads, 0, c->stream>>>(dSegs, dTileSegs, leaf, dTiles, dGroups, dStage, dStageTop, dSegWeights);
     scan_color_tiles_kernel<<<(nTiles + kTileGroup - 1) / kTileGroup, kTileGroup, 0, c->stream>>>(dTiles, nTiles, dGroups, dOffsets, dTotals, weights_out, weights_out ? weights_capacity : 0);
     HDT_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->launches += 3;
@@ -1670,7 +1678,7 @@ int hdt_rebuild_color_leaf(hdt_ctx* c, const hdt_color_leaf* old_leaf, size_t ol
         return fail(HDT_ERR_CAPACITY, "hdt_rebuild_color_leaf: an output buffer is too small (see counts_out)");
     if ((counts_out[1] && !weights_out) || !blocks_out || !macro_blocks_out) return fail(HDT_ERR_ARG, "hdt_rebuild_color_leaf: null output buffer");
     HDT_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    color_pieces_kernel<true><<<nTiles, kPieceThreads, 0, c->stream>>>(dSegs, dTileSegs, leaf, nullptr, nullptr, dOffsets, weights_out, blocks_out, macro_blocks_out);
+    color_emit_kernel<<<nTiles, kEmitThreads, 0, c->stream>>>(dSegWeights, dTileSegs, dTiles, dStage, dOffsets, leaf, weights_out, blocks_out, macro_blocks_out);
     HDT_CUDA(cudaEventRecord(c->ev[3], c->stream));
     ++c->launches;
     HDT_CUDA(cudaStreamSynchronize(c->stream));
