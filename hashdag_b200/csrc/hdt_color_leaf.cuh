@@ -16,14 +16,18 @@
 // the new leaf.  Inside a piece (colorBits, bitsPerWeight) is constant, so
 //   * a block of the new leaf starts at a piece iff the piece starts a macro block or its key differs from the piece
 //     before it (blocks the old leaf had split at ITS macro boundaries, or at an op boundary, merge again this way);
-//   * the weights of a COPY piece are a contiguous bit range of the old stream, moved to their new bit position with
-//     funnel shifts, 32 bits at a time; a FILL piece is a periodic pattern.
-// Work per piece, not per colour: the bench leaf has 15.5 colours per block.  Kernels, one CTA per macro block of the new leaf:
-//   1. count_color_pieces_kernel  enumerate the pieces, reduce {blocks started, weight bits};
-//   2. scan_color_tiles_kernel    exclusive scan of those pairs (one CTA; a leaf has n/16384 macro blocks);
-//   3. emit_color_pieces_kernel   enumerate the pieces again, CTA-wide scan, block headers, macro-block pairs, the weight bits
-//                                 assembled in shared memory and stored as whole swapped words (the two words a macro block
-//                                 may share with its neighbours go through atomicOr).
+//   * the weights need not be moved piece by piece: the pieces of a COPY segment (op x new macro block) are consecutive blocks of
+//     the old leaf, so its weights are one contiguous bit range of the old stream per old macro block it touches (at most two),
+//     moved with funnel shifts one destination word at a time; a FILL segment is a periodic pattern.
+// Work per piece, not per colour: the bench leaf has 15.5 colours per block.  Kernels:
+//   1. color_segments_kernel     one warp per macro block of the new leaf: the ops that reach into it, and for every COPY
+//                                segment the old blocks of its first and last colour (the searches);
+//   2. color_pieces_kernel       one CTA per macro block: the pieces, once -- CTA-wide scans of {blocks started, weight bits},
+//                                finished block entries (they only hold positions relative to the macro block) staged in
+//                                scratch memory, every segment's weight range, the macro block's {blocks, bits};
+//   3. scan_color_tiles_kernel   first block index and weight bit offset of every macro block;
+//   4. color_emit_kernel         one CTA per macro block, nothing per piece: staged entries to their place, macro-block pairs,
+//                                weight words (the words two macro blocks share go through atomicOr).
 // Bit-exact with the reference builder by construction; pinned against leaves the reference built
 // (tests/golden/ref_color_leaves_d13.npz, tests/test_gpu_color_leaf.py).
 #pragma once
