@@ -234,18 +234,22 @@ __device__ __forceinline__ u32 read_stream_bits(const ColorLeafDev& l, u64 p, u3
 }
 
 // A piece as a thread keeps it between the two halves of a round: colorBits, and
-// first colour within the new macro block (14 bits) | bitsPerWeight << 14 | colours << 17.
-__device__ __forceinline__ u32 pack_piece(u32 dstLocal, u32 bpw, u32 len) { return dstLocal | (bpw << 14) | (len << 17); }
+// first colour within the new macro block (14 bits) | colours << 14 (15 bits) | bitsPerWeight << 29.
+__device__ __forceinline__ u32 pack_piece(u32 dstLocal, u32 bpw, u32 len) { return dstLocal | (len << 14) | (bpw << 29); }
 __device__ __forceinline__ u32 piece_dst(u32 pk) { return pk & 0x3FFF; }
-__device__ __forceinline__ u32 piece_bpw(u32 pk) { return (pk >> 14) & 7; }
-__device__ __forceinline__ u32 piece_bits(u32 pk) { return (pk >> 17) * piece_bpw(pk); }
+__device__ __forceinline__ u32 piece_bpw(u32 pk) { return pk >> 29; }
+__device__ __forceinline__ u32 piece_bits(u32 pk) { return ((pk >> 14) & 0x7FFF) * piece_bpw(pk); }
 __device__ __forceinline__ u64 piece_key(u32 colorBits, u32 pk) { return u64(colorBits) | (u64(piece_bpw(pk)) << 32); }   // equal keys continue a block
 
 // Piece of a COPY segment that comes from block `b` of the old leaf (`blk`; `nextLocal` = first colour of block b + 1 within its
 // macro block).  Colour indices are relative to the old macro block of the segment's first colour: the segment is
-// [src0, src0 + len) there, at most 16384 long, so it ends before 2 * 16384.  -> packed piece; srcAt = where its first weight
-// bit sits in the old stream.
-__device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, u32 nextLocal, u64& srcAt)
+// [src0, src0 + len) there, at most 16384 long, so it ends before 2 * 16384.  -> packed piece; skipped = colours of the block in
+// front of the piece (piece_src_at: where the piece's first weight bit sits in the old stream).
+__device__ __forceinline__ u64 piece_src_at(const SegmentDev& sg, u32 b, u32 hdr, u32 skipped)
+{
+    return (b > sg.last0 ? sg.weightBase[1] : sg.weightBase[0]) + (hdr >> 16) + skipped * block_bits_per_weight(hdr);
+}
+__device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, u32 nextLocal, u32& skipped)
 {
     const u32 second = b > sg.last0 ? 1u : 0u;
     const u32 hdr = u32(blk), startLocal = hdr & 0x3FFF;
@@ -254,7 +258,7 @@ __device__ __forceinline__ u32 copy_piece(const SegmentDev& sg, u32 b, u64 blk, 
     const u32 blockStart = base + startLocal, blockEnd = base + (nextLocal > startLocal ? nextLocal : u32(kColorsPerMacroBlock));
     const u32 ps = max(blockStart, sg.src0), pe = min(blockEnd, sg.src0 + sg.len);
     const u32 bpw = block_bits_per_weight(hdr);
-    srcAt = (second ? sg.weightBase[1] : sg.weightBase[0]) + (hdr >> 16) + (ps - blockStart) * bpw;
+    skipped = ps - blockStart;
     return pack_piece(sg.dstLocal + (ps - sg.src0), bpw, pe - ps);
 }
 
@@ -346,11 +350,12 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
 #pragma unroll
                 for (u32 j = 0; j < K; ++j) {
                     if (j < nMine) {
-                        u64 srcAt;
-                        pk[j] = copy_piece(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, srcAt);
+                        u32 skipped;
+                        pk[j] = copy_piece(sg, b + j, blk[j], u32(blk[j + 1]) & 0x3FFF, skipped);
                         cb[j] = u32(blk[j] >> 32);
                         const u32 bits = piece_bits(pk[j]), half = b + j > sg.last0 ? 1u : 0u;
                         if (bits && !(haveAt & (1u << half))) {
+                            const u64 srcAt = piece_src_at(sg, b + j, u32(blk[j]), skipped);
                             if (half) at1 = srcAt - myBits; else at0 = srcAt - myBits;
                             haveAt |= 1u << half;
                         }
@@ -374,8 +379,8 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                             const u32 b = sg.block0 + (p - pieceStart);
                             const u64 blk = __ldg(oldLeaf.blocks + b);
                             const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
-                            u64 srcAt;
-                            pk[j] = copy_piece(sg, b, blk, nextLocal, srcAt);
+                            u32 skipped;
+                            pk[j] = copy_piece(sg, b, blk, nextLocal, skipped);
                             cb[j] = u32(blk >> 32);
                         } else {
                             pk[j] = pack_piece(sg.dstLocal, (sg.fill >> 8) & 0xFF, sg.len);
@@ -449,9 +454,9 @@ __global__ void __launch_bounds__(kPieceThreads, HDT_PIECE_MIN_BLOCKS) color_pie
                                 if (bits) {      // where the old stream continues for this half: the same from every piece of it
                                     const u64 blk = __ldg(oldLeaf.blocks + b);
                                     const u32 nextLocal = (u64(b) + 1 < oldLeaf.nBlocks) ? (u32(__ldg(oldLeaf.blocks + b + 1)) & 0x3FFF) : 0u;
-                                    u64 srcAt;
-                                    copy_piece(sg, b, blk, nextLocal, srcAt);
-                                    segDelta[half][s] = srcAt - bit;
+                                    u32 skipped;
+                                    copy_piece(sg, b, blk, nextLocal, skipped);
+                                    segDelta[half][s] = piece_src_at(sg, b, u32(blk), skipped) - bit;
                                 }
                             }
                             if (p == pieceStart) segBit0[s] = bit;
