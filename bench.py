@@ -189,7 +189,7 @@ def product_implementation(args, world):
         "beam_prefetch": not getattr(args, "no_beam_prefetch", False),
         "hash_dag_pointers": "resolved pool + prefix pool (hdt_hash_dag_resolve: child pointers pre-translated, sibling voxel counts pre-summed)" if resolved else "as stored",
         "colors": "from the ancestor records of the paths pass (HDT_OPT_COLORS_RECORDED)" if resolved and os.environ.get("HDT_COLORS_RECORDED", "1") != "0" else "full DAG walk",
-        "frames_in_flight": 2 if world > 1 else getattr(args, "frames_in_flight", 1),
+        "frames_in_flight": max(2, int(os.environ.get("HDT_BENCH_LANES", "2"))) if world > 1 else getattr(args, "frames_in_flight", 1),
     }
 
 
@@ -322,10 +322,13 @@ def run_ours(args):
         class _Mem:
             def __init__(self, ptr, count):
                 self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-        tr2 = tracer.DAGTracer(True, W, H, args.levels, device=local_rank)
-        tr2.set_partition(rank, world, tile_log2)
-        lanes = [tr, tr2]
-        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        n_lanes = max(2, int(os.environ.get("HDT_BENCH_LANES", "2")))     # frames in flight per rank
+        lanes = [tr]
+        for _ in range(n_lanes - 1):
+            t2 = tracer.DAGTracer(True, W, H, args.levels, device=local_rank)
+            t2.set_partition(rank, world, tile_log2)
+            lanes.append(t2)
+        streams = [torch.cuda.Stream(device=dev) for _ in lanes]
         mine, gathered, frames = [], [], []
         for t_, s_ in zip(lanes, streams):
             _, cptr, n_owned, max_tiles = t_.partition_buffers()
