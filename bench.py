@@ -173,7 +173,7 @@ def workload_config(args, scene, W, H, world):
         "levels": args.levels, "resolution": [W, H], "voxels": int(scene.n_voxels), "dag_words": int(scene.basic.size),
         "hash_pool_mib": round(scene.hash_pool.nbytes / 2**20, 1) if scene.has_hash else 0,
         "color_mib": round((scene.weights.nbytes + scene.blocks.nbytes + scene.macro_blocks.nbytes) / 2**20, 1),
-        "partition": "whole frame" if world == 1 else f"64x64 screen tiles, tile t -> rank t % {world}, replicated DAG, " + ("NCCL gather to rank 0" if getattr(args, "exchange", "peer") == "nccl" else "tiles stored into rank 0's frame over NVLink peer memory"),
+        "partition": "whole frame" if world == 1 else f"{1 << int(os.environ.get('HDT_BENCH_TILE_LOG2', '6'))}x{1 << int(os.environ.get('HDT_BENCH_TILE_LOG2', '6'))} screen tiles, tile t -> rank t % {world}, replicated DAG, " + ("NCCL gather to rank 0" if getattr(args, "exchange", "peer") == "nccl" else "tiles stored into rank 0's frame over NVLink peer memory"),
         "l2_policy": "inputs larger than L2: each step is a different camera pose over a DAG pool >> 126 MB",
         "shadow_bias": 1.0, "fog_density": 0.0,
         "scene_generator": "hashdag_b200/scene/scene_builder.cpp: seeded value-noise terrain + spheres (NOT the reference's FastNoise, src/FastNoise.cpp; "
@@ -301,7 +301,7 @@ def run_ours(args):
     info = camera.DAGInfo(*bounds)
 
     tr = tracer.DAGTracer(True, W, H, args.levels, device=local_rank)
-    tile_log2 = 6
+    tile_log2 = int(os.environ.get("HDT_BENCH_TILE_LOG2", "6"))     # partition tiles of 64x64 pixels
     if world > 1:
         tr.set_partition(rank, world, tile_log2)
     params = [camera.trace_params(p, info, args.levels, W, H) for p in poses]
