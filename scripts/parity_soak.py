@@ -2,6 +2,7 @@
 and axis-parallel directions), HashDAG (plain and resolved + prefix pool) and BasicDAG.  Prints one JSON line.
 
     python scripts/parity_soak.py [--poses 150] [--seed 1]
+    python scripts/parity_soak.py --reference d13|d17 [--poses 150]      # against the REFERENCE's kernels (oracle/_ref), own process per scene
 """
 import argparse
 import json
@@ -46,13 +47,64 @@ def random_poses(rng, scene, footprint_log2, n):
     return poses
 
 
+def reference_soak(a):
+    """Product and oracle against the reference's own kernels (oracle/_ref, 256x256 variants) on the recipe scene `a.reference`."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as gu
+    from hashdag_b200 import camera, tracer
+    from oracle import hdo, ref
+    scene = gu.recipe_scene(a.reference)
+    info = camera.DAGInfo(scene.bounds_min, scene.bounds_max)
+    rt = ref.RefTracer(scene.levels, gu.W, gu.H)
+    rt.load_scene(scene)
+    t = tracer.DAGTracer(True, gu.W, gu.H, scene.levels)
+    rng = np.random.default_rng(a.seed * 77 + scene.levels)
+    poses = random_poses(rng, scene, gu.RECIPES[a.reference]["footprint_log2"], a.poses)
+    hd = tracer.HashDAG.from_scene(scene)
+    cases = [("basic", 0, 1, tracer.BasicDAG.from_scene(scene), tracer.BasicDAGCompressedColors.from_scene(scene), hdo.make_dag(scene, hdo.DAG_BASIC), hdo.make_colors(scene, hdo.COLORS_COMPRESSED))]
+    if scene.has_hash_colors:
+        cases.append(("hash resolved + prefix", 1, 3, t.resolve_hash_dag(hd), tracer.HashDAGColors.from_scene(scene), hdo.make_dag(scene, hdo.DAG_HASH), hdo.make_colors(scene, hdo.COLORS_HASH)))
+    rep = {"reference_scene": a.reference, "poses_per_case": a.poses, "resolution": [gu.W, gu.H], "cases": [], "mismatched_pixels": 0, "fog_max_channel_diff": 0}
+    for name, dk, ck, dag, col, odag, ocol in cases:
+        bad_cuda = bad_oracle = hits = fog = 0
+        for cam in poses:
+            prm = camera.trace_params(cam, info, scene.levels, gu.W, gu.H)
+            rt.resolve_paths(dk, cam, info); rp = rt.read_paths()
+            rt.resolve_colors(dk, ck); rc = rt.read_colors()
+            rt.resolve_shadows(dk, cam, info, 1.0, 0.0); rs = rt.read_colors()
+            rt.resolve_colors(dk, ck)
+            rt.resolve_shadows(dk, cam, info, 2.5, 5.0); rf = rt.read_colors()
+            t.resolve_paths(cam, info, dag); p = t.read_paths()
+            t.resolve_colors(dag, col); c = t.read_colors()
+            t.resolve_shadows(cam, info, dag, 1.0, 0.0); sh = t.read_colors()
+            t.resolve_colors(dag, col)
+            t.resolve_shadows(cam, info, dag, 2.5, 5.0); fg = t.read_colors()
+            op, st = hdo.trace_paths(odag, gu.W, gu.H, prm)
+            oc, _ = hdo.trace_colors(odag, ocol, op)
+            osh, _ = hdo.trace_shadows(odag, prm, op, oc, 1.0, 0.0)
+            hits += int(st["n_hit"])
+            bad_cuda += int((p != rp).any(-1).sum()) + int((c != rc).sum()) + int((sh != rs).sum())
+            bad_oracle += int((op != rp).any(-1).sum()) + int((oc != rc).sum()) + int((osh != rs).sum())
+            fog = max(fog, int(np.abs(fg.view(np.uint8).astype(np.int16) - rf.view(np.uint8).astype(np.int16)).max()))
+        rep["cases"].append({"dag": name, "hit_pixels": hits, "cuda_vs_reference_kernels": bad_cuda, "oracle_vs_reference_kernels": bad_oracle, "fog_max_channel_diff": fog})
+        rep["mismatched_pixels"] += bad_cuda + bad_oracle
+        rep["fog_max_channel_diff"] = max(rep["fog_max_channel_diff"], fog)
+        print(rep["cases"][-1], file=sys.stderr, flush=True)
+    t.close()
+    rt.close()
+    print("PARITY_SOAK " + json.dumps(rep), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="", help="recipe scene (d13, d17): compare with the reference's kernels instead of the oracle only")
     ap.add_argument("--poses", type=int, default=150)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--width", type=int, default=320)
     ap.add_argument("--height", type=int, default=200)
     a = ap.parse_args()
+    if a.reference:
+        return reference_soak(a)
     from hashdag_b200 import camera, tracer
     from hashdag_b200.scene import build_scene
     from oracle import hdo
